@@ -261,14 +261,23 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
       if (note_is_deleted(back)) continue;
       if (back->namesz != pn->namesz || memcmp(back->name, pn->name, pn->namesz) != 0) break;
       if (back->start == pn->start && back->end == pn->end) { pn->type = 0; break; } /* rule 2 */
-      /* rule 3: overlapping or adjoining (within 16 bytes up to alignment) ranges are merged */
-      if (pn->start <= back->end && pn->end >= back->start) {
-        back->start = back->start < pn->start ? back->start : pn->start;
-        back->end = back->end > pn->end ? back->end : pn->end;
-        pn->type = 0;
-        break;
+      /* a note whose range lies inside an earlier same-name note's range is redundant
+       * (objcopy.c contained_by(pnote, back)) */
+      if (pn->start >= back->start && pn->end <= back->end) { pn->type = 0; break; }
+      /* rule 3: objcopy.c overlaps_or_adjoins(back, pnote), restated as published -- including its
+       * inverted gap test: when back ends before pnote starts the ranges are merged iff there IS
+       * a gap after rounding back's end up to 16; otherwise they merge unless both ends are equal. */
+      {
+        int merge;
+        if (back->end < pn->start) merge = (((back->end + 15) & ~(uint64_t)15) < pn->start);
+        else merge = (back->end != pn->end);
+        if (merge) {
+          back->start = back->start < pn->start ? back->start : pn->start;
+          back->end = back->end > pn->end ? back->end : pn->end;
+          pn->type = 0;
+          break;
+        }
       }
-      if (((back->end + 15) & ~(uint64_t)15) + 1 >= pn->start && back->end <= pn->end && 0) { /* placeholder */ }
       if (iter++ > 16) break;
     }
   }
