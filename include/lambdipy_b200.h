@@ -1,0 +1,154 @@
+/*
+ * lambdipy_b200.h -- C ABI of the B200 (sm_100a) ELF strip library, liblambdipy_b200.so.
+ *
+ * What it replaces.  The reference (customink/lambdipy) has no FFI for this step: it strips the
+ * build tree by running one shell line inside a generated script,
+ *
+ *     find {install_dir}/ -name "*.so" | xargs strip        /root/reference/lambdipy/project_build.py:260
+ *
+ * executed by install_non_resolved_requirements() (project_build.py:234-277; Popen at :268, docker
+ * exec at :274) before the script is removed (:277).  The entry points below are what a ctypes
+ * binding placed at that spot calls instead (see INTEGRATION.md for the reference-side stub):
+ *
+ *   lb2_strip_tree()          == the whole shell line: select basename "*.so" under a root
+ *                                (find, :260), strip each regular ELF in place (strip, :260),
+ *                                preserving mode, replacing via temp file + rename.
+ *   lb2_strip_host()          == `strip` over a batch of files already read into host memory
+ *                                (what xargs hands to one strip process), results to host memory.
+ *   lb2_strip_device_async()  == the same batch with input and output arenas resident in HBM
+ *                                (benchmark / pipeline building block).
+ *
+ * Result contract: for every file with status LB2_ST_OK the output bytes are identical to
+ * `strip --strip-unneeded -o OUT IN` of GNU Binutils 2.42 (== flagless `strip` for ET_DYN/ET_EXEC).
+ * Files the device planner does not cover get a positive status and no output; lb2_strip_tree can
+ * hand exactly those to the host `strip` binary (LB2_TREE_FALLBACK_HOST_STRIP) so the tree ends up
+ * identical to the reference's, and reports how many took that route.
+ *
+ * Conventions: plain C types; the caller owns every buffer it passes; the library keeps no pointer
+ * past a call except where stated (async call: until lb2_batch_results); functions return 0 on
+ * success or a negative LB2_E_* code and never throw; one context per thread and device.
+ * There is no CPU implementation behind this ABI: without a CUDA device lb2_ctx_create fails.
+ */
+#ifndef LAMBDIPY_B200_H
+#define LAMBDIPY_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lb2_ctx lb2_ctx;
+
+/* library return codes */
+enum {
+  LB2_OK = 0,
+  LB2_E_CUDA = -1,        /* CUDA runtime error; text in lb2_last_error */
+  LB2_E_ARG = -2,         /* bad argument (NULL, unaligned offsets, ...) */
+  LB2_E_CAPACITY = -3,    /* output arena too small; stats.out_bytes_needed says how much */
+  LB2_E_IO = -4,          /* filesystem error in lb2_strip_tree */
+  LB2_E_NODEVICE = -5,    /* no usable CUDA device */
+  LB2_E_STATE = -6        /* call out of order (no batch in flight, ...) */
+};
+
+/* per-file status written by the plan kernel */
+enum {
+  LB2_ST_OK = 0,
+  LB2_ST_NOT_ELF = 1,            /* GNU strip: "file format not recognized" */
+  LB2_ST_NOT_ELF64LE = 2,
+  LB2_ST_BAD_TYPE = 3,           /* ET_REL, ET_CORE ... */
+  LB2_ST_NO_SECTIONS = 4,        /* GNU strip: "has no sections" */
+  LB2_ST_XINDEX = 5,
+  LB2_ST_UNSUPPORTED_LAYOUT = 6, /* a layout rule the planner does not implement */
+  LB2_ST_BAD_NOTES = 7,          /* corrupt .gnu.build.attributes (objcopy refuses too) */
+  LB2_ST_PLANNER_LIMIT = 8,      /* > 64 sections, > 32 phdrs, > 2 KB of section names, > 8 KB notes */
+  LB2_ST_MALFORMED = -1
+};
+
+/* flags for the strip calls */
+#define LB2_F_NO_MERGE_NOTES 1u /* behave like `strip --no-merge-notes` */
+
+/* flags for lb2_strip_tree */
+#define LB2_TREE_FALLBACK_HOST_STRIP 0x100u /* unsupported ELF files: run the host `strip` on them  */
+#define LB2_TREE_TOLERATE_NON_ELF    0x200u /* non-ELF "*.so": leave untouched (reference: rc 123)   */
+#define LB2_TREE_DRY_RUN             0x400u /* plan + compact, write nothing                         */
+
+typedef struct lb2_stats {
+  uint32_t n_files, n_ok, n_unsupported, overflow;
+  uint64_t in_bytes;          /* input bytes of the n_ok files                                  */
+  uint64_t out_bytes;         /* OUT: stripped bytes written                                    */
+  uint64_t copy_bytes;        /* C:   extent bytes read (input arena + regenerated literals)    */
+  uint64_t header_bytes;      /* H:   header/table/note bytes the planner parsed                */
+  uint64_t n_tiles;
+  uint64_t out_bytes_needed;  /* 256-byte-rounded arena bytes the batch needs                   */
+  float plan_ms;              /* plan + offset scan kernels, CUDA events on the call's stream   */
+  float compact_ms;           /* compaction kernel                                              */
+  float h2d_ms, d2h_ms;       /* lb2_strip_host only: summed copy time                          */
+} lb2_stats;
+
+typedef struct lb2_tree_stats {
+  uint32_t n_selected;        /* paths whose basename ends in the suffix                        */
+  uint32_t n_gpu;             /* replaced with GPU-produced bytes                               */
+  uint32_t n_fallback;        /* handed to the host `strip`                                     */
+  uint32_t n_skipped;         /* symlinks, directories, tolerated non-ELF                       */
+  uint32_t n_failed;          /* would make the reference's script exit non-zero                */
+  uint32_t pad;
+  uint64_t in_bytes, out_bytes;
+  double walk_read_s, gpu_s, write_s, fallback_s;
+  lb2_stats batch;
+} lb2_tree_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int lb2_ctx_create(int device, lb2_ctx **ctx);
+void lb2_ctx_destroy(lb2_ctx *ctx);
+const char *lb2_last_error(const lb2_ctx *ctx); /* ctx may be NULL: error of the failed create */
+const char *lb2_version(void);
+int lb2_sm_count(const lb2_ctx *ctx);
+
+/* ---- device / pinned memory for callers without their own CUDA runtime (ctypes) ---------- */
+void *lb2_dev_alloc(lb2_ctx *ctx, uint64_t bytes);
+void lb2_dev_free(lb2_ctx *ctx, void *p);
+void *lb2_pinned_alloc(lb2_ctx *ctx, uint64_t bytes);
+void lb2_pinned_free(lb2_ctx *ctx, void *p);
+int lb2_memcpy_h2d(lb2_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
+int lb2_memcpy_d2h(lb2_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
+int lb2_memset_d(lb2_ctx *ctx, void *d_dst, int value, uint64_t bytes);
+
+/* ---- strip a batch resident in HBM ------------------------------------------------------ */
+/* d_in: input arena; file f occupies [h_in_off[f], h_in_off[f+1]) minus padding -- offsets must be
+ * multiples of 16 and h_in_sizes[f] gives the exact byte length (NULL: use the offset difference).
+ * d_out: output arena of out_capacity bytes; file f lands at out_off[f] (multiples of 256).
+ * Enqueues upload of the offsets, the plan kernel, the offset scan and the compaction kernel on
+ * `stream` (a cudaStream_t; NULL = the context's own stream) and returns without synchronising. */
+int lb2_strip_device_async(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                           uint32_t n_files, void *d_out, uint64_t out_capacity, uint32_t flags, void *stream);
+/* Waits for the batch, copies offsets/status back.  Any pointer may be NULL. */
+int lb2_batch_results(lb2_ctx *ctx, uint64_t *h_out_off /* n+1 */, uint64_t *h_out_sizes /* n */,
+                      int32_t *h_status /* n */, lb2_stats *stats);
+
+/* ---- strip a batch held in host memory (H2D + kernels + D2H, pipelined in chunks) -------- */
+/* h_out_off[f] (multiples of 256) and h_out_sizes[f] describe where file f was written in h_out. */
+int lb2_strip_host(lb2_ctx *ctx, const void *h_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                   uint32_t n_files, void *h_out, uint64_t out_capacity, uint64_t *h_out_off, uint64_t *h_out_sizes,
+                   int32_t *h_status, uint32_t flags, lb2_stats *stats);
+
+/* ---- strip a directory tree in place (the reference's shell line) ------------------------ */
+int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix /* ".so" */, uint32_t flags,
+                   lb2_tree_stats *stats);
+
+/* ---- plan only: per-file output sizes and status, nothing copied (tests) ------------------ */
+int lb2_plan_device(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                    uint32_t n_files, uint32_t flags, uint64_t *h_out_sizes, int32_t *h_status, lb2_stats *stats);
+
+/* ---- synthetic corpus: fill payload regions of an HBM arena with counter-based random bytes - */
+typedef struct lb2_fill_region {
+  uint64_t offset; /* byte offset in the arena */
+  uint64_t len;
+} lb2_fill_region;
+/* byte at arena offset o = byte (o & 7) of splitmix64(seed + (o >> 3)); independent of the region
+ * split, so host and device generators agree. */
+int lb2_corpus_fill(lb2_ctx *ctx, void *d_arena, const lb2_fill_region *h_regions, uint32_t n_regions,
+                    uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

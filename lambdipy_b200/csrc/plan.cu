@@ -1,0 +1,900 @@
+// plan.cu -- the ELF "plan" kernel: one warp per file parses Ehdr / Shdr / Phdr / .shstrtab out of
+// the HBM input arena with coalesced 16-byte loads, decides keep/drop per section (warp ballot),
+// lays the stripped file out exactly as GNU strip (Binutils 2.42) would, regenerates .shstrtab,
+// the section-header table, the program-header table and merged build-attribute notes into a
+// per-file scratch slot, and emits the list of (src,dst,len) tiles the compaction kernel executes.
+//
+// Replaces, per file, what the reference delegates to the external `strip` binary:
+// /root/reference/lambdipy/project_build.py:260.  Rules R1..R12: /root/repo/SURVEY.md 8(c).
+// This is product code: it shares nothing with oracle/ (an independent CPU restatement used only
+// by the tests to check this kernel).
+#include "lb2_common.cuh"
+
+namespace lb2 {
+
+struct DNote {
+  uint64_t start, end;
+  uint32_t type;
+  uint16_t off;     // offset of the note header inside note_buf
+  uint16_t namesz;
+};
+
+struct PlanSmem {
+  Ehdr eh;
+  Shdr sh[MAX_SH];
+  Phdr ph[MAX_PH];
+  Phdr nph[MAX_PH];
+  uint64_t new_off[MAX_SH];
+  uint64_t new_size[MAX_SH];
+  uint64_t src_addr[MAX_SH];  // absolute device address of the section's bytes (input or scratch)
+  uint64_t ext_src[MAX_EXT], ext_dst[MAX_EXT], ext_len[MAX_EXT];
+  uint32_t ext_tiles[MAX_EXT];
+  uint32_t ent_off[MAX_SH + 1];
+  uint16_t ent_str[MAX_SH + 1];
+  uint16_t ent_len[MAX_SH + 1];
+  int16_t ent_host[MAX_SH + 1];
+  uint8_t ent_sorted[MAX_SH + 1];
+  uint8_t sec_ent[MAX_SH];
+  int8_t seg[MAX_SH];
+  uint8_t keep[MAX_SH];
+  uint8_t new_index[MAX_SH];
+  uint8_t order[MAX_SH + 1];
+  uint8_t pkeep[MAX_PH];
+  uint8_t piece[MAX_SH];
+  char names[MAX_STR + 16];
+  DNote notes[MAX_NOTES];
+  uint16_t note_perm[MAX_NOTES];
+  uint16_t note_tmp[MAX_NOTES];
+  uint8_t note_buf[MAX_NOTE_BYTES];
+  // scalars shared by the warp
+  int fail;
+  int nk, nent, n_ext, new_phnum, note_tie;
+  uint32_t strsz, new_strsz;
+  uint64_t cur, shstr_off, new_shoff, total, hdr_bytes;
+};
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ uint64_t lowbit(uint64_t v) { return v & (~v + 1); }
+__device__ __forceinline__ uint64_t align_up(uint64_t v, uint64_t a) { return a > 1 ? (v + a - 1) / a * a : v; }
+
+__device__ __forceinline__ int d_strlen(const char *s) { int n = 0; while (s[n]) n++; return n; }
+__device__ __forceinline__ bool d_streq(const char *a, const char *b) {
+  for (int i = 0;; i++) { if (a[i] != b[i]) return false; if (!a[i]) return true; }
+}
+__device__ __forceinline__ bool d_prefix(const char *s, const char *p) {
+  for (int i = 0; p[i]; i++) if (s[i] != p[i]) return false;
+  return true;
+}
+
+// Warp-cooperative global->shared copy.  16-byte vector loads when both sides allow it (the
+// Shdr table of a BFD/ld/lld-written file sits at an 8- or 16-aligned e_shoff and every file
+// base in the arena is 16-aligned), 8-byte, then byte loads otherwise.
+__device__ __forceinline__ void warp_g2s(void *dst_s, const uint8_t *src_g, uint32_t nbytes, int lane) {
+  uintptr_t s = reinterpret_cast<uintptr_t>(src_g);
+  uint8_t *d = static_cast<uint8_t *>(dst_s);
+  if (((s | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    uint32_t nv = nbytes >> 4;
+    for (uint32_t i = lane; i < nv; i += 32)
+      reinterpret_cast<uint4 *>(d)[i] = __ldg(reinterpret_cast<const uint4 *>(src_g) + i);
+    for (uint32_t i = (nv << 4) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  } else if (((s | reinterpret_cast<uintptr_t>(d)) & 7) == 0) {
+    uint32_t nv = nbytes >> 3;
+    for (uint32_t i = lane; i < nv; i += 32)
+      reinterpret_cast<uint2 *>(d)[i] = __ldg(reinterpret_cast<const uint2 *>(src_g) + i);
+    for (uint32_t i = (nv << 3) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  } else {
+    for (uint32_t i = lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  }
+}
+
+// R1: BFD marks these non-alloc names SEC_DEBUGGING; strip removes them.
+__device__ bool is_debug_name(const char *n) {
+  return d_prefix(n, ".debug") || d_prefix(n, ".zdebug") || d_prefix(n, ".gnu.debuglto_.debug_") ||
+         d_prefix(n, ".gnu.linkonce.wi.") || d_prefix(n, ".line") || d_prefix(n, ".stab") || d_streq(n, ".gdb_index");
+}
+
+// BFD ELF_SECTION_IN_SEGMENT (check_vma, !strict): which sections a program header carries.
+__device__ bool sec_in_seg(const Shdr &s, const Phdr &p) {
+  const uint32_t t = p.p_type;
+  const bool tls = (s.sh_flags & SHF_TLS) != 0, alloc = (s.sh_flags & SHF_ALLOC) != 0;
+  const uint64_t sz = (tls && s.sh_type == SHT_NOBITS && t != PT_TLS) ? 0 : s.sh_size;
+  if (tls) { if (!(t == PT_TLS || t == PT_GNU_RELRO || t == PT_LOAD)) return false; }
+  else if (t == PT_TLS || t == PT_PHDR) return false;
+  if (!alloc && (t == PT_LOAD || t == PT_DYNAMIC || t == PT_GNU_EH_FRAME || t == PT_GNU_STACK || t == PT_GNU_RELRO ||
+                 t == PT_GNU_SFRAME || (t >= PT_GNU_MBIND_LO && t <= PT_GNU_MBIND_HI)))
+    return false;
+  if (s.sh_type != SHT_NOBITS) {
+    if (s.sh_offset < p.p_offset) return false;
+    if (s.sh_offset - p.p_offset + sz > p.p_filesz) return false;
+  }
+  if (alloc) {
+    if (s.sh_addr < p.p_vaddr) return false;
+    if (s.sh_addr - p.p_vaddr + sz > p.p_memsz) return false;
+  }
+  if ((t == PT_DYNAMIC || t == PT_NOTE) && s.sh_size == 0 && p.p_memsz != 0) {
+    bool ok_off = s.sh_type == SHT_NOBITS || (s.sh_offset > p.p_offset && s.sh_offset - p.p_offset < p.p_filesz);
+    bool ok_vma = !alloc || (s.sh_addr > p.p_vaddr && s.sh_addr - p.p_vaddr < p.p_memsz);
+    if (!(ok_off && ok_vma)) return false;
+  }
+  return true;
+}
+
+// elf-strtab.c strrevcmp on two names held in sm.names
+__device__ int strrev_cmp(const char *a, int la, const char *b, int lb) {
+  int l = la < lb ? la : lb;
+  const unsigned char *s = reinterpret_cast<const unsigned char *>(a) + la - 1;
+  const unsigned char *t = reinterpret_cast<const unsigned char *>(b) + lb - 1;
+  while (l--) {
+    if (*s != *t) return (int)*s - (int)*t;
+    s--, t--;
+  }
+  return la - lb;
+}
+
+// ---------------------------------------------------------------- R9: objcopy merge_gnu_build_notes
+__device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+__device__ __forceinline__ void wr32(uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; }
+__device__ __forceinline__ void wr64(uint8_t *p, uint64_t v) { wr32(p, (uint32_t)v); wr32(p + 4, (uint32_t)(v >> 32)); }
+
+__device__ __forceinline__ bool note_is_version(const PlanSmem &sm, const DNote &n) {
+  const uint8_t *nm = sm.note_buf + n.off + 12;
+  return n.namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1;
+}
+
+// first sort: by attribute name, then by range (objcopy.c compare_gnu_build_notes)
+__device__ int cmp_by_attr(PlanSmem &sm, const DNote &a, const DNote &b) {
+  const uint8_t *n1 = sm.note_buf + a.off + 12, *n2 = sm.note_buf + b.off + 12;
+  int l = (int)(a.namesz < b.namesz ? a.namesz : b.namesz) - 3;
+  for (int i = 0; i < l; i++)
+    if (n1[3 + i] != n2[3 + i]) return (int)n1[3 + i] - (int)n2[3 + i];
+  if (a.namesz != b.namesz) sm.note_tie = 1;  // order would depend on libc's merge sequence: refuse
+  if (a.end < b.start) return -1;
+  if (a.start > b.end) return 1;
+  if (a.start < b.start) return -1;
+  if (a.end > b.end) return 1;
+  if (a.end < b.end) return -1;
+  if (a.type == 0x100 && b.type != 0x100) return -1;
+  if (a.type != 0x100 && b.type == 0x100) return 1;
+  return 0;
+}
+// second sort: by address range (objcopy.c sort_gnu_build_notes)
+__device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
+  if (a.start < b.start) return -1;
+  if (a.start > b.start) return 1;
+  if (a.end > b.end) return -1;
+  if (a.end < b.end) return 1;
+  if (a.type == 0x100 && b.type != 0x100) return -1;
+  if (a.type != 0x100 && b.type == 0x100) return 1;
+  bool v1 = note_is_version(sm, a), v2 = note_is_version(sm, b);
+  if (v1 && !v2) return -1;
+  if (!v1 && v2) return 1;
+  return 0;
+}
+
+// Stable sort of the note permutation by rank counting, one element per lane-iteration:
+// rank(i) = #{j : cmp(j,i) < 0} + #{j < i : cmp(j,i) == 0}  (== glibc 2.39's stable merge
+// sort for a consistent comparator).  `second` selects the comparator.
+__device__ void warp_sort_notes(PlanSmem &sm, int n, bool second, int lane) {
+  for (int i = lane; i < n; i += 32) sm.note_tmp[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const DNote &me = sm.notes[sm.note_perm[i]];
+    int r = 0;
+    for (int j = 0; j < n; j++) {
+      if (j == i) continue;
+      const DNote &o = sm.notes[sm.note_perm[j]];
+      int c = second ? cmp_by_addr(sm, o, me) : cmp_by_attr(sm, o, me);
+      if (c < 0 || (c == 0 && j < i)) r++;
+    }
+    sm.note_tmp[r] = sm.note_perm[i];
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) sm.note_perm[i] = sm.note_tmp[i];
+  __syncwarp();
+}
+
+// Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
+// Returns the new size; *err != 0 when objcopy would report corrupt notes.  Warp-collective.
+__device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out, int *err, int lane) {
+  __shared__ int s_n, s_err, s_skip;
+  __shared__ uint32_t s_newsize;
+  if (lane == 0) {
+    s_err = 0; s_skip = 0; s_n = 0;
+    int n = 0;
+    uint32_t remain = size, p = 0;
+    unsigned v1 = 0, v2 = 0, v3 = 0;
+    uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
+    while (remain >= 12) {
+      if (n >= MAX_NOTES) { s_err = 2; break; }
+      const uint8_t *h = sm.note_buf + p;
+      uint32_t namesz = rd32(h), descsz = rd32(h + 4), type = rd32(h + 8);
+      uint32_t padded = (namesz + 3) & ~3u;
+      if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
+      if (type != 0x100 && type != 0x101) { s_err = 1; break; }
+      if ((uint64_t)padded + descsz + 12 > remain) { s_err = 1; break; }
+      if (namesz < 2) { s_err = 1; break; }
+      const uint8_t *nm = h + 12, *desc = h + 12 + padded;
+      remain -= 12 + padded + descsz;
+      p += 12 + padded + descsz;
+      DNote &d = sm.notes[n];
+      d.off = (uint16_t)(h - sm.note_buf);
+      d.namesz = (uint16_t)namesz;
+      d.type = type;
+      if (namesz > 2 && nm[0] == '$' && nm[1] == 1 && nm[2] == '1') v1++;
+      else if (namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) {
+        if (nm[4] == '2') v2++;
+        else if (nm[4] == '3') v3++;
+        else { s_err = 1; break; }
+      }
+      uint64_t start, end;
+      if (descsz == 0) start = end = 0;
+      else if (descsz == 4) { start = rd32(desc); end = ~0ull; }
+      else if (descsz == 8) { start = rd32(desc); end = rd32(desc + 4); }
+      else if (descsz == 16) { start = rd64(desc); end = rd64(desc + 8); }
+      else { s_err = 1; break; }
+      if (start > end) start = end;
+      if (type == 0x100) {
+        if (start) pos = start;
+        d.start = pos;
+        if (end) poe = end;
+        d.end = poe;
+      } else {
+        if (start) pfs = start;
+        d.start = pfs;
+        if (end) pfe = end;
+        d.end = pfe;
+      }
+      if (nm[namesz - 1] != 0) { s_err = 1; break; }
+      sm.note_perm[n] = (uint16_t)n;
+      n++;
+    }
+    if (!s_err && remain != 0) s_err = 1;
+    if (!s_err) {
+      if (v1 == 0 && v2 == 0 && v3 == 0) v3 = 2;
+      if ((v1 && v2) || (v1 && v3) || (v2 && v3)) s_err = 1;
+      else if (v3 == 0) s_skip = 1;
+    }
+    s_n = n;
+  }
+  __syncwarp();
+  if (s_err) { *err = s_err; return size; }
+  if (s_skip || size < 12) {
+    for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+    return size;
+  }
+  const int n = s_n;
+  warp_sort_notes(sm, n, false, lane);
+  if (sm.note_tie) { *err = 3; return size; }  // name ties of unequal length: order is libc-specific
+  if (lane == 0) {
+    for (int i = 0; i < n; i++) {
+      DNote &pn = sm.notes[sm.note_perm[i]];
+      if (pn.type == 0) continue;
+      if (pn.start == pn.end) { pn.type = 0; continue; }
+      int iter = 0;
+      for (int b = i - 1; b >= 0; b--) {
+        DNote &back = sm.notes[sm.note_perm[b]];
+        if (back.type == 0) continue;
+        if (back.namesz != pn.namesz) break;
+        const uint8_t *n1 = sm.note_buf + back.off + 12, *n2 = sm.note_buf + pn.off + 12;
+        bool same = true;
+        for (int q = 0; q < pn.namesz; q++) if (n1[q] != n2[q]) { same = false; break; }
+        if (!same) break;
+        if (back.start == pn.start && back.end == pn.end) { pn.type = 0; break; }
+        if (pn.start >= back.start && pn.end <= back.end) { pn.type = 0; break; }
+        bool merge;
+        if (back.end < pn.start) merge = (((back.end + 15) & ~15ull) < pn.start);
+        else merge = (back.end != pn.end);
+        if (merge) {
+          if (pn.start < back.start) back.start = pn.start;
+          if (pn.end > back.end) back.end = pn.end;
+          pn.type = 0;
+          break;
+        }
+        if (iter++ > 16) break;
+      }
+    }
+  }
+  __syncwarp();
+  warp_sort_notes(sm, n, true, lane);
+  if (lane == 0) {
+    uint32_t w = 0;
+    uint64_t ps = 0, pe = 0;
+    for (int i = 0; i < n; i++) {
+      const DNote &pn = sm.notes[sm.note_perm[i]];
+      if (pn.type == 0) continue;
+      bool elide = (pn.start == ps && pn.end == pe);
+      uint32_t padded = (pn.namesz + 3u) & ~3u;
+      wr32(out + w, pn.namesz);
+      wr32(out + w + 4, elide ? 0u : 16u);
+      wr32(out + w + 8, pn.type);
+      w += 12;
+      const uint8_t *nm = sm.note_buf + pn.off + 12;
+      for (uint32_t q = 0; q < padded; q++) out[w + q] = q < pn.namesz ? nm[q] : 0;
+      w += padded;
+      if (!elide) {
+        wr64(out + w, pn.start);
+        wr64(out + w + 8, pn.end);
+        w += 16;
+        ps = pn.start;
+        pe = pn.end;
+      }
+    }
+    s_newsize = w;
+  }
+  __syncwarp();
+  if (s_newsize < size) return s_newsize;
+  for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+  __syncwarp();
+  return size;
+}
+
+#define LB2_FAIL(code) do { sm.fail = (code); } while (0)
+
+__global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
+  __shared__ PlanSmem sm;
+  const int lane = threadIdx.x;
+  const uint32_t f = blockIdx.x;
+  if (f >= a.n_files) return;
+  const uint64_t base = a.in_off[f];
+  const uint64_t n = a.in_size[f];
+  const uint8_t *in = a.in + base;
+  uint8_t *scr = a.scratch + (uint64_t)f * SCR_STRIDE;
+
+  if (lane == 0) { sm.fail = 0; sm.note_tie = 0; }
+  __syncwarp();
+
+  // ---- A. Ehdr
+  if (n < 64) { if (lane == 0) { a.status[f] = ST_NOT_ELF; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  if (lane < 4) reinterpret_cast<uint4 *>(&sm.eh)[lane] = __ldg(reinterpret_cast<const uint4 *>(in) + lane);
+  __syncwarp();
+  const Ehdr &eh = sm.eh;
+  int st = ST_OK;
+  if (!(eh.e_ident[0] == 0x7f && eh.e_ident[1] == 'E' && eh.e_ident[2] == 'L' && eh.e_ident[3] == 'F')) st = ST_NOT_ELF;
+  else if (eh.e_ident[4] != 2 || eh.e_ident[5] != 1) st = ST_NOT_ELF64LE;
+  else if (eh.e_type != 2 && eh.e_type != 3) st = ST_BAD_TYPE;
+  else if (eh.e_machine != 62 && eh.e_machine != 183) st = ST_UNSUPPORTED_LAYOUT;
+  else if (eh.e_shoff == 0 || eh.e_shnum == 0) st = ST_NO_SECTIONS;
+  else if (eh.e_shentsize != 64 || (eh.e_phnum && eh.e_phentsize != 56)) st = ST_MALFORMED;
+  else if (eh.e_shstrndx == 0xffff || eh.e_shnum >= 0xff00 || eh.e_phnum == 0xffff) st = ST_XINDEX;
+  else if (eh.e_shoff > n || (uint64_t)eh.e_shnum * 64 > n - eh.e_shoff) st = ST_MALFORMED;
+  else if (eh.e_phoff > n || (uint64_t)eh.e_phnum * 56 > n - eh.e_phoff) st = ST_MALFORMED;
+  else if (eh.e_shstrndx >= eh.e_shnum) st = ST_MALFORMED;
+  else if (eh.e_phnum && eh.e_phoff != 64) st = ST_UNSUPPORTED_LAYOUT;
+  else if (eh.e_shnum > MAX_SH || eh.e_phnum > MAX_PH) st = ST_PLANNER_LIMIT;
+  if (st != ST_OK) { if (lane == 0) { a.status[f] = st; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  const int shnum = eh.e_shnum, phnum = eh.e_phnum;
+
+  // ---- B. section headers, program headers, section names: coalesced vector loads into smem
+  warp_g2s(sm.sh, in + eh.e_shoff, (uint32_t)shnum * 64, lane);
+  if (phnum) warp_g2s(sm.ph, in + eh.e_phoff, (uint32_t)phnum * 56, lane);
+  __syncwarp();
+  {
+    const Shdr &strh = sm.sh[eh.e_shstrndx];
+    if (strh.sh_type != SHT_STRTAB || strh.sh_offset > n || strh.sh_size > n - strh.sh_offset || strh.sh_size == 0) st = ST_MALFORMED;
+    else if (strh.sh_size > MAX_STR) st = ST_PLANNER_LIMIT;
+    if (st != ST_OK) { if (lane == 0) { a.status[f] = st; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+    const uint32_t strsz = (uint32_t)strh.sh_size;
+    // byte loads unless the table happens to be 16-aligned (it rarely is; it is <= 2 KB)
+    warp_g2s(sm.names, in + strh.sh_offset, strsz, lane);
+    if (lane < 10) sm.names[strsz + lane] = ".shstrtab"[lane];  // literal appended behind the table
+    if (lane == 0) { sm.strsz = strsz; sm.hdr_bytes = (uint64_t)shnum * 64 + strsz + (uint64_t)phnum * 56 + 64; }
+    __syncwarp();
+    if (sm.names[strsz - 1] != 0) { if (lane == 0) { a.status[f] = ST_MALFORMED; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  }
+  const uint32_t strsz = sm.strsz;
+
+  // ---- C. R1 keep/drop mask, lane i <-> sections i and i+32; verdicts combined by ballot
+  {
+    int err_mal = 0, err_uns = 0;
+    for (int i = lane; i < shnum; i += 32) {
+      Shdr &h = sm.sh[i];
+      sm.keep[i] = 0; sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
+      sm.src_addr[i] = reinterpret_cast<uint64_t>(in) + h.sh_offset;
+      if (h.sh_name >= strsz) { err_mal = 1; continue; }
+      if (h.sh_type != SHT_NOBITS && h.sh_type != SHT_NULL && (h.sh_offset > n || h.sh_size > n - h.sh_offset)) { err_mal = 1; continue; }
+      if (i == 0) { sm.keep[0] = 1; continue; }
+      const char *nm = sm.names + h.sh_name;
+      const bool alloc = (h.sh_flags & SHF_ALLOC) != 0;
+      bool drop = false;
+      if (h.sh_type == SHT_SYMTAB || h.sh_type == SHT_SYMTAB_SHNDX) drop = true;
+      else if (h.sh_type == SHT_STRTAB && !alloc) drop = true;
+      else if (!alloc && is_debug_name(nm)) drop = true;
+      if (h.sh_type == SHT_NULL || h.sh_type == SHT_GROUP) err_uns = 1;
+      if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
+      if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
+      if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
+      sm.keep[i] = drop ? 0 : 1;
+      // BFD keeps a power-of-two alignment the address honours: min(lowbit(align), lowbit(addr))
+      uint64_t al = h.sh_addralign ? lowbit(h.sh_addralign) : 1;
+      if (h.sh_addr) { uint64_t lb = lowbit(h.sh_addr); if (lb < al) al = lb; }
+      h.sh_addralign = al;
+    }
+    unsigned mal = __ballot_sync(0xffffffffu, err_mal), uns = __ballot_sync(0xffffffffu, err_uns);
+    if (mal || uns) { if (lane == 0) { a.status[f] = mal ? ST_MALFORMED : ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  }
+  __syncwarp();
+
+  // ---- D. R2 output order (hoist of a later dynsym in front of the first section linking to
+  //         it ... BFD: in front of the first REL/RELA that uses it) and new section indices.
+  if (lane == 0) {
+    uint64_t emitted = 0;
+    int nk = 0;
+    for (int i = 0; i < shnum; i++) {
+      if (!sm.keep[i] || ((emitted >> i) & 1)) continue;
+      const Shdr &h = sm.sh[i];
+      if ((h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && h.sh_link < (uint32_t)shnum && (int)h.sh_link > i &&
+          sm.keep[h.sh_link] && !((emitted >> h.sh_link) & 1) &&
+          (sm.sh[h.sh_link].sh_type == SHT_DYNSYM || sm.sh[h.sh_link].sh_type == SHT_SYMTAB)) {
+        sm.order[nk++] = (uint8_t)h.sh_link;
+        emitted |= 1ull << h.sh_link;
+      }
+      sm.order[nk++] = (uint8_t)i;
+      emitted |= 1ull << i;
+    }
+    for (int k = 0; k < nk; k++) sm.new_index[sm.order[k]] = (uint8_t)k;
+    sm.nk = nk;
+  }
+  __syncwarp();
+  const int nk = sm.nk;
+
+  // ---- E. R9 build-attribute note merging (sizes feed the layout)
+  if (!(a.flags & 1u)) {
+    uint32_t scr_used = 0;
+    for (int i = 1; i < shnum; i++) {
+      const Shdr &h = sm.sh[i];
+      if (!sm.keep[i] || h.sh_type != SHT_NOTE || (h.sh_flags & SHF_ALLOC)) continue;
+      if (!d_prefix(sm.names + h.sh_name, ".gnu.build.attributes")) continue;
+      if (h.sh_size > MAX_NOTE_BYTES || scr_used + h.sh_size > MAX_NOTE_BYTES) { if (lane == 0) LB2_FAIL(ST_PLANNER_LIMIT); break; }
+      warp_g2s(sm.note_buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
+      __syncwarp();
+      int err = 0;
+      uint8_t *dst = scr + SCR_NOTES + scr_used;
+      uint32_t ns = merge_build_notes(sm, (uint32_t)h.sh_size, dst, &err, lane);
+      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? ST_PLANNER_LIMIT : err == 3 ? ST_UNSUPPORTED_LAYOUT : ST_BAD_NOTES); break; }
+      if (lane == 0) {
+        sm.new_size[i] = ns;
+        sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
+        sm.hdr_bytes += h.sh_size;
+      }
+      scr_used += (ns + 15u) & ~15u;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+
+  // ---- F. which PT_LOAD carries each kept alloc section (lane-parallel), which phdrs survive (R11)
+  {
+    int err = 0;
+    for (int i = 1 + lane; i < shnum; i += 32) {
+      if (!sm.keep[i] || !(sm.sh[i].sh_flags & SHF_ALLOC)) continue;
+      int sg = -1;
+      for (int j = 0; j < phnum; j++)
+        if (sm.ph[j].p_type == PT_LOAD && sec_in_seg(sm.sh[i], sm.ph[j])) { sg = j; break; }
+      if (sg < 0) err = 1;
+      sm.seg[i] = (int8_t)sg;
+    }
+    if (__ballot_sync(0xffffffffu, err)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  }
+  __syncwarp();
+  {
+    int keepj = 1;
+    if (lane < phnum) {
+      if (sm.ph[lane].p_type == PT_LOAD && sm.ph[lane].p_offset != 0) {
+        int members = 0;
+        for (int i = 1; i < shnum; i++) members += (sm.keep[i] && sm.seg[i] == lane);
+        if (!members) keepj = 0;
+      }
+      sm.pkeep[lane] = (uint8_t)keepj;
+      sm.nph[lane] = sm.ph[lane];
+    }
+    unsigned km = __ballot_sync(0xffffffffu, lane < phnum && keepj);
+    if (lane == 0) sm.new_phnum = __popc(km);
+  }
+  __syncwarp();
+  const int new_phnum = sm.new_phnum;
+
+  // ---- G. R10: PT_LOAD layout (sequential in the file cursor)
+  if (lane == 0) {
+    uint64_t cur = 64 + (uint64_t)new_phnum * 56, last_vaddr = 0;
+    for (int j = 0; j < phnum && !sm.fail; j++) {
+      const Phdr &p = sm.ph[j];
+      if (p.p_type != PT_LOAD || !sm.pkeep[j]) continue;
+      if (p.p_vaddr < last_vaddr) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); break; }
+      last_vaddr = p.p_vaddr;
+      const bool first = (p.p_offset == 0);
+      bool contents = false;
+      for (int i = 1; i < shnum; i++) if (sm.keep[i] && sm.seg[i] == j && sm.sh[i].sh_type != SHT_NOBITS) contents = true;
+      uint64_t new_off = 0;
+      if (!first) { uint64_t al = p.p_align ? p.p_align : 1; new_off = cur + ((p.p_vaddr - cur) % al); }
+      uint64_t off = first ? cur : new_off;
+      uint64_t mem_end = p.p_vaddr + (first ? cur : 0), file_end = off;
+      int idx = 0;
+      for (int i = 1; i < shnum; i++) {
+        if (!sm.keep[i] || sm.seg[i] != j) continue;
+        const Shdr &h = sm.sh[i];
+        uint64_t want = new_off + (h.sh_addr - p.p_vaddr);
+        if (h.sh_type != SHT_NOBITS) {
+          if (want < off) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); break; }
+          off = want;
+          sm.new_off[i] = off;
+          off += sm.new_size[i];
+          file_end = off;
+        } else {
+          if (idx == 0) off = want;
+          sm.new_off[i] = off;
+        }
+        if (!(h.sh_type == SHT_NOBITS && (h.sh_flags & SHF_TLS))) {
+          uint64_t e = h.sh_addr + h.sh_size;
+          if (e > mem_end) mem_end = e;
+        }
+        idx++;
+      }
+      Phdr &q = sm.nph[j];
+      q.p_offset = new_off;
+      if (!contents && !first) {
+        uint64_t al = p.p_align > 0x1000 ? p.p_align : 0x1000;
+        q.p_offset = cur % al;
+        q.p_filesz = 0;
+      } else {
+        q.p_filesz = file_end - new_off;
+      }
+      q.p_memsz = mem_end - p.p_vaddr;
+      if (contents || first) cur = file_end;
+    }
+    sm.cur = cur;
+  }
+  __syncwarp();
+  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+
+  // ---- H. R12: every other program header, one per lane
+  if (lane < phnum && sm.pkeep[lane] && sm.ph[lane].p_type != PT_LOAD) {
+    const int j = lane;
+    const Phdr &p = sm.ph[j];
+    Phdr &q = sm.nph[j];
+    const uint32_t t = p.p_type;
+    if (t == PT_PHDR) {
+      q.p_filesz = q.p_memsz = (uint64_t)new_phnum * 56;
+    } else {
+      int first = -1, last_bits = -1;
+      for (int i = 1; i < shnum; i++) {
+        if (!sm.keep[i] || !sec_in_seg(sm.sh[i], p)) continue;
+        if (first < 0) first = i;
+        if (sm.sh[i].sh_type != SHT_NOBITS) last_bits = i;
+      }
+      if (t == PT_GNU_STACK) { q.p_offset = 0; q.p_filesz = 0; }
+      else if (t == PT_GNU_RELRO) {
+        bool ok = false;
+        if (first >= 0) {
+          const uint64_t start = sm.sh[first].sh_addr, end = start + p.p_memsz;
+          for (int l = 0; l < phnum && !ok; l++) {
+            if (sm.ph[l].p_type != PT_LOAD || !sm.pkeep[l]) continue;
+            int lf = -1, ll = -1;
+            for (int i = 1; i < shnum; i++) if (sm.keep[i] && sm.seg[i] == l) { if (lf < 0) lf = i; ll = i; }
+            if (lf < 0) continue;
+            const Shdr &hl = sm.sh[ll];
+            uint64_t lend = hl.sh_addr + ((hl.sh_type == SHT_NOBITS && (hl.sh_flags & SHF_TLS)) ? 0 : hl.sh_size);
+            if (!(lend > start && sm.sh[lf].sh_addr < end)) continue;
+            for (int i = 1; i < shnum; i++) {
+              if (!sm.keep[i] || sm.seg[i] != l) continue;
+              const Shdr &h = sm.sh[i];
+              if (h.sh_addr >= start && h.sh_addr < end && h.sh_size != 0) {
+                q.p_vaddr = h.sh_addr;
+                q.p_paddr = h.sh_addr + (sm.ph[l].p_paddr - sm.ph[l].p_vaddr);
+                q.p_offset = sm.new_off[i];
+                q.p_memsz = end - q.p_vaddr;
+                q.p_filesz = q.p_memsz;
+                const Phdr &nl = sm.nph[l];
+                if (q.p_filesz > nl.p_vaddr + nl.p_filesz - q.p_vaddr) q.p_filesz = nl.p_vaddr + nl.p_filesz - q.p_vaddr;
+                ok = true;
+                break;
+              }
+            }
+            break;
+          }
+        }
+        if (!ok) { q.p_type = 0; q.p_flags = 0; q.p_offset = q.p_vaddr = q.p_paddr = q.p_filesz = q.p_memsz = q.p_align = 0; }
+      } else if (first < 0) {
+        q.p_offset = 0; q.p_filesz = 0; q.p_memsz = 0;
+      } else {
+        q.p_offset = sm.new_off[first];
+        q.p_filesz = 0;
+        if (t == PT_TLS) {  // p_memsz := address extent of .tdata/.tbss (gold rounds its value up)
+          uint64_t end = p.p_vaddr;
+          for (int i = 1; i < shnum; i++)
+            if (sm.keep[i] && sec_in_seg(sm.sh[i], p) && sm.sh[i].sh_addr + sm.sh[i].sh_size > end) end = sm.sh[i].sh_addr + sm.sh[i].sh_size;
+          q.p_memsz = end - p.p_vaddr;
+        }
+        if (last_bits >= 0) {
+          q.p_filesz = sm.new_off[last_bits] - q.p_offset + sm.new_size[last_bits];
+          if (t == PT_NOTE && (sm.sh[last_bits].sh_flags & SHF_ALLOC)) q.p_memsz = q.p_filesz;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- I. R4 non-alloc sections packed behind the last allocated byte (align-then-add chain)
+  if (lane == 0) {
+    uint64_t cur = sm.cur;
+    for (int k = 1; k < nk; k++) {
+      const int i = sm.order[k];
+      const Shdr &h = sm.sh[i];
+      if (h.sh_flags & SHF_ALLOC) continue;
+      cur = align_up(cur, h.sh_addralign ? h.sh_addralign : 1);
+      sm.new_off[i] = cur;
+      if (h.sh_type != SHT_NOBITS) cur += sm.new_size[i];
+    }
+    sm.cur = cur;
+  }
+  __syncwarp();
+
+  // ---- J. R6 .shstrtab: unique names (entry 0 = ".shstrtab"), reversed-string rank sort across
+  //         lanes, suffix merge, offsets in insertion order.
+  for (int k = 1 + lane; k < nk; k += 32) {
+    const int i = sm.order[k];
+    const char *nm = sm.names + sm.sh[i].sh_name;
+    int first = k;
+    if (d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
+    else for (int q = 1; q < k; q++) if (d_streq(nm, sm.names + sm.sh[sm.order[q]].sh_name)) { first = q; break; }
+    sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int nent = 0;
+    sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; nent = 1;
+    for (int k = 1; k < nk; k++) {
+      const int i = sm.order[k];
+      if (sm.piece[k] == k && sm.names[sm.sh[i].sh_name] != 0) {
+        sm.ent_str[nent] = (uint16_t)sm.sh[i].sh_name;
+        sm.ent_len[nent] = (uint16_t)d_strlen(sm.names + sm.sh[i].sh_name);
+        sm.sec_ent[i] = (uint8_t)nent;
+        nent++;
+      } else if (sm.names[sm.sh[i].sh_name] == 0) {
+        sm.sec_ent[i] = 0xff;  // empty name -> sh_name 0
+      } else {
+        sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
+      }
+    }
+    sm.nent = nent;
+  }
+  __syncwarp();
+  const int nent = sm.nent;
+  for (int e = lane; e < nent; e += 32) {
+    int r = 0;
+    for (int o = 0; o < nent; o++)
+      if (o != e && strrev_cmp(sm.names + sm.ent_str[o], sm.ent_len[o], sm.names + sm.ent_str[e], sm.ent_len[e]) < 0) r++;
+    sm.ent_sorted[r] = (uint8_t)e;  // names are unique => ranks are a permutation
+    sm.ent_host[e] = -1;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int cur = sm.ent_sorted[nent - 1];
+    for (int s = nent - 2; s >= 0; s--) {
+      const int c = sm.ent_sorted[s];
+      const int lc = sm.ent_len[c], lh = sm.ent_len[cur];
+      bool suffix = lh > lc;
+      if (suffix) {
+        const char *hs = sm.names + sm.ent_str[cur] + (lh - lc), *cs = sm.names + sm.ent_str[c];
+        for (int q = 0; q < lc; q++) if (hs[q] != cs[q]) { suffix = false; break; }
+      }
+      if (suffix) sm.ent_host[c] = (int16_t)cur;
+      else cur = c;
+    }
+    uint32_t size = 1;
+    for (int e = 0; e < nent; e++) if (sm.ent_host[e] < 0) { sm.ent_off[e] = size; size += sm.ent_len[e] + 1u; }
+    for (int e = 0; e < nent; e++) if (sm.ent_host[e] >= 0) { int h = sm.ent_host[e]; sm.ent_off[e] = sm.ent_off[h] + (sm.ent_len[h] - sm.ent_len[e]); }
+    sm.new_strsz = size;
+    // R5
+    sm.shstr_off = sm.cur;
+    sm.new_shoff = align_up(sm.cur + size, 8);
+    sm.total = sm.new_shoff + (uint64_t)(nk + 1) * 64;
+  }
+  __syncwarp();
+  const uint32_t new_strsz = sm.new_strsz;
+  if (new_strsz > MAX_STR + 16) { if (lane == 0) { a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  // blob: zero, then every non-merged name at its offset
+  for (uint32_t i = lane; i < ((new_strsz + 15u) & ~15u); i += 32) scr[SCR_STR + i] = 0;
+  __syncwarp();
+  for (int e = lane; e < nent; e += 32)
+    if (sm.ent_host[e] < 0) {
+      const char *s = sm.names + sm.ent_str[e];
+      for (int q = 0; q < sm.ent_len[e]; q++) scr[SCR_STR + sm.ent_off[e] + q] = (uint8_t)s[q];
+    }
+
+  // ---- K. R7 new section-header table (one header per lane-iteration), R8 Ehdr, new Phdr table
+  for (int k = lane; k <= nk; k += 32) {
+    Shdr h;
+    if (k == 0) {
+      h.sh_name = 0; h.sh_type = 0; h.sh_flags = 0; h.sh_addr = 0; h.sh_offset = 0; h.sh_size = 0; h.sh_link = 0;
+      h.sh_info = 0; h.sh_addralign = 0; h.sh_entsize = 0;  // BFD writes a fresh all-zero NULL header
+    } else if (k == nk) {
+      h.sh_name = sm.ent_off[0]; h.sh_type = SHT_STRTAB; h.sh_flags = 0; h.sh_addr = 0; h.sh_offset = sm.shstr_off;
+      h.sh_size = new_strsz; h.sh_link = 0; h.sh_info = 0; h.sh_addralign = 1; h.sh_entsize = 0;
+    } else {
+      const int i = sm.order[k];
+      h = sm.sh[i];
+      const char *nm = sm.names + h.sh_name;
+      h.sh_name = sm.sec_ent[i] == 0xff ? 0 : sm.ent_off[sm.sec_ent[i]];
+      h.sh_offset = sm.new_off[i];
+      h.sh_size = sm.new_size[i];
+      if (h.sh_link && h.sh_link < (uint32_t)shnum) h.sh_link = sm.keep[h.sh_link] ? sm.new_index[h.sh_link] : 0;
+      if ((h.sh_flags & SHF_INFO_LINK) && h.sh_info && h.sh_info < (uint32_t)shnum)
+        h.sh_info = sm.keep[h.sh_info] ? sm.new_index[h.sh_info] : 0;
+      if (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) {
+        // BFD re-derives the section a dynamic reloc section applies to from its name
+        const char *t = nullptr;
+        if (d_prefix(nm, ".rela")) t = nm + 5;
+        else if (d_prefix(nm, ".rel")) t = nm + 4;
+        int target = -1;
+        if (t && *t) {
+          if (d_streq(t, ".plt")) {
+            for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, ".got.plt")) { target = q; break; }
+            if (target < 0) for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, ".got")) { target = q; break; }
+          } else {
+            for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, t)) { target = q; break; }
+          }
+        }
+        if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
+      }
+      switch (h.sh_type) {  // elf_fake_sections(): entsize of the types BFD knows
+        case SHT_INIT_ARRAY: case SHT_FINI_ARRAY: case SHT_PREINIT_ARRAY: h.sh_entsize = 8; break;
+        case SHT_HASH: h.sh_entsize = 4; break;
+        case SHT_DYNAMIC: h.sh_entsize = 16; break;
+        case SHT_GNU_HASH: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED: h.sh_entsize = 0; break;
+        default: break;
+      }
+    }
+    *reinterpret_cast<Shdr *>(scr + SCR_SHDR + (uint32_t)k * 64) = h;
+  }
+  if (lane == 0) {
+    Ehdr ne = sm.eh;
+    ne.e_shoff = sm.new_shoff;
+    ne.e_shnum = (uint16_t)(nk + 1);
+    ne.e_shstrndx = (uint16_t)nk;
+    ne.e_phnum = (uint16_t)new_phnum;
+    *reinterpret_cast<Ehdr *>(scr + SCR_EHDR) = ne;
+    uint32_t w = 64;
+    for (int j = 0; j < phnum; j++)
+      if (sm.pkeep[j]) {
+        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(&sm.nph[j]);
+        uint64_t *d8 = reinterpret_cast<uint64_t *>(scr + w);
+        for (int q = 0; q < 7; q++) d8[q] = s8[q];
+        w += 56;
+      }
+  }
+
+  // ---- L. extents: every output byte is produced exactly once -- copied from the input arena,
+  //         copied from the scratch slot, or zero-filled (BFD leaves gaps as file holes).
+  if (lane == 0) {
+    // content sections sorted by their new offset (insertion sort; inputs are nearly sorted)
+    int np = 0;
+    for (int k = 1; k < nk; k++) {
+      const int i = sm.order[k];
+      if (sm.sh[i].sh_type == SHT_NOBITS || sm.new_size[i] == 0) continue;
+      int q = np++;
+      while (q > 0 && sm.new_off[sm.piece[q - 1]] > sm.new_off[i]) { sm.piece[q] = sm.piece[q - 1]; q--; }
+      sm.piece[q] = (uint8_t)i;
+    }
+    int ne = 0;
+    uint64_t pos = 0, copy_bytes = 0;
+    auto emit = [&](uint64_t src, uint64_t dst, uint64_t len) {
+      if (len == 0 || sm.fail) return;
+      if (dst < pos) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); return; }
+      if (dst > pos) { sm.ext_src[ne] = 0; sm.ext_dst[ne] = pos; sm.ext_len[ne] = dst - pos; ne++; }
+      sm.ext_src[ne] = src; sm.ext_dst[ne] = dst; sm.ext_len[ne] = len; ne++;
+      pos = dst + len;
+      copy_bytes += len;
+    };
+    emit(reinterpret_cast<uint64_t>(scr + SCR_EHDR), 0, 64 + (uint64_t)new_phnum * 56);
+    for (int q = 0; q < np; q++) { const int i = sm.piece[q]; emit(sm.src_addr[i], sm.new_off[i], sm.new_size[i]); }
+    emit(reinterpret_cast<uint64_t>(scr + SCR_STR), sm.shstr_off, new_strsz);
+    emit(reinterpret_cast<uint64_t>(scr + SCR_SHDR), sm.new_shoff, (uint64_t)(nk + 1) * 64);
+    sm.n_ext = ne;
+    sm.cur = copy_bytes;
+  }
+  __syncwarp();
+  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+
+  // ---- M. tiles: warp-shuffle prefix sum over the per-extent tile counts gives every extent its
+  //         slot range in the global tile list; one atomicAdd per file reserves the range.
+  const int n_ext = sm.n_ext;
+  __shared__ unsigned long long s_tile_base;
+  uint32_t running = 0;
+  for (int e0 = 0; e0 < n_ext; e0 += 32) {
+    const int e = e0 + lane;
+    uint32_t cnt = 0;
+    if (e < n_ext) {
+      const uint64_t d = sm.ext_dst[e], l = sm.ext_len[e];
+      cnt = (uint32_t)((d + l - 1) / TILE_BYTES - d / TILE_BYTES + 1);
+    }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (e < n_ext) sm.ext_tiles[e] = running + inc - cnt;  // exclusive prefix
+    running += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) s_tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);
+  __syncwarp();
+  const unsigned long long tile_base = s_tile_base;
+  if (tile_base + running > a.tile_cap) {
+    if (lane == 0) { a.ctr->overflow = 1; a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; }
+    return;
+  }
+  for (int e = 0; e < n_ext; e++) {
+    const uint64_t d = sm.ext_dst[e], l = sm.ext_len[e], s = sm.ext_src[e];
+    const uint64_t t0 = d / TILE_BYTES;
+    const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - t0 + 1);
+    Tile *out = a.tiles + tile_base + sm.ext_tiles[e];
+    for (uint32_t k = lane; k < cnt; k += 32) {
+      uint64_t b = (t0 + k) * TILE_BYTES, en = b + TILE_BYTES;
+      if (b < d) b = d;
+      if (en > d + l) en = d + l;
+      Tile t;
+      t.src = s ? s + (b - d) : 0;
+      t.dst_rel = b;
+      t.len = (uint32_t)(en - b);
+      t.file = f;
+      out[k] = t;
+    }
+  }
+  if (lane == 0) {
+    a.out_size[f] = sm.total;
+    a.status[f] = ST_OK;
+    atomicAdd(&a.ctr->copy_bytes, (unsigned long long)sm.cur);
+    atomicAdd(&a.ctr->out_bytes, (unsigned long long)sm.total);
+    atomicAdd(&a.ctr->header_bytes, (unsigned long long)sm.hdr_bytes);
+    atomicAdd(&a.ctr->in_bytes, (unsigned long long)n);
+    atomicAdd(&a.ctr->n_ok, 1u);
+  }
+}
+
+// ---------------------------------------------------------------- output offsets
+// Exclusive scan of the 256-byte-rounded output sizes: where each stripped file starts in the
+// output arena.  One CTA; n_files is at most a few 10^5.
+__global__ void __launch_bounds__(1024) lb2_scan_kernel(const uint64_t *out_size, uint64_t *out_off, uint32_t n,
+                                                         uint64_t out_cap, BatchCounters *ctr) {
+  __shared__ uint64_t warp_excl[32];
+  __shared__ uint64_t carry, block_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint64_t v = i < n ? ((out_size[i] + 255) & ~255ull) : 0;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_excl[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      const uint64_t w = warp_excl[lane];
+      uint64_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      warp_excl[lane] = winc - w;
+      if (lane == 31) block_total = winc;
+    }
+    __syncthreads();
+    if (i < n) out_off[i] = carry + warp_excl[wid] + inc - v;
+    __syncthreads();
+    if (tid == 0) carry += block_total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out_off[n] = carry;
+    if (carry > out_cap) ctr->overflow = 1;
+  }
+}
+
+void launch_plan(const PlanArgs &a, cudaStream_t s) {
+  if (a.n_files) lb2_plan_kernel<<<a.n_files, 32, 0, s>>>(a);
+}
+void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, cudaStream_t s) {
+  lb2_scan_kernel<<<1, 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr);
+}
+
+}  // namespace lb2

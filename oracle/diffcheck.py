@@ -83,6 +83,7 @@ def main():
     ap.add_argument("--no-merge", action="store_true")
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("-v", action="store_true")
+    ap.add_argument("--all", action="store_true", help="every regular file, not only *.so*")
     ap.add_argument("paths", nargs="+")
     a = ap.parse_args()
     files = []
@@ -90,7 +91,7 @@ def main():
         if os.path.isdir(p):
             for d, _, fs in os.walk(p):
                 for f in fs:
-                    if ".so" in f and not os.path.islink(os.path.join(d, f)):
+                    if (a.all or ".so" in f) and not os.path.islink(os.path.join(d, f)):
                         files.append(os.path.join(d, f))
         else:
             files.append(p)

@@ -598,6 +598,14 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
     if (first < 0) { NP[j].p_offset = 0; NP[j].p_filesz = 0; NP[j].p_memsz = 0; continue; }
     NP[j].p_offset = S[first].new_off;
     NP[j].p_filesz = 0;
+    if (t == PT_TLS) {
+      /* BFD recomputes PT_TLS p_memsz as the address extent of .tdata/.tbss (gold rounds the
+       * input value up to the alignment; probe: -fuse-ld=gold fixture 0x40 -> 0x31) */
+      uint64_t end = P[j].p_vaddr;
+      for (uint64_t i = 1; i < shnum; i++)
+        if (S[i].keep && sec_in_seg(&in_hdr[i], &P[j]) && S[i].h.sh_addr + S[i].h.sh_size > end) end = S[i].h.sh_addr + S[i].h.sh_size;
+      NP[j].p_memsz = end - P[j].p_vaddr;
+    }
     if (last_bits >= 0) {
       NP[j].p_filesz = S[last_bits].new_off - NP[j].p_offset + S[last_bits].new_size;
       if (t == PT_NOTE && (S[last_bits].h.sh_flags & SHF_ALLOC)) NP[j].p_memsz = NP[j].p_filesz;
