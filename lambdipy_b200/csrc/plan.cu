@@ -145,12 +145,11 @@ __device__ __forceinline__ bool note_is_version(const PlanSmem &sm, const DNote 
 }
 
 // first sort: by attribute name, then by range (objcopy.c compare_gnu_build_notes)
-__device__ int cmp_by_attr(PlanSmem &sm, const DNote &a, const DNote &b) {
+__device__ int cmp_by_attr(const PlanSmem &sm, const DNote &a, const DNote &b) {
   const uint8_t *n1 = sm.note_buf + a.off + 12, *n2 = sm.note_buf + b.off + 12;
   int l = (int)(a.namesz < b.namesz ? a.namesz : b.namesz) - 3;
   for (int i = 0; i < l; i++)
     if (n1[3 + i] != n2[3 + i]) return (int)n1[3 + i] - (int)n2[3 + i];
-  if (a.namesz != b.namesz) sm.note_tie = 1;  // order would depend on libc's merge sequence: refuse
   if (a.end < b.start) return -1;
   if (a.start > b.end) return 1;
   if (a.start < b.start) return -1;
@@ -174,26 +173,33 @@ __device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
   return 0;
 }
 
-// Stable sort of the note permutation by rank counting, one element per lane-iteration:
-// rank(i) = #{j : cmp(j,i) < 0} + #{j < i : cmp(j,i) == 0}  (== glibc 2.39's stable merge
-// sort for a consistent comparator).  `second` selects the comparator.
-__device__ void warp_sort_notes(PlanSmem &sm, int n, bool second, int lane) {
-  for (int i = lane; i < n; i += 32) sm.note_tmp[i] = 0;
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) {
-    const DNote &me = sm.notes[sm.note_perm[i]];
-    int r = 0;
-    for (int j = 0; j < n; j++) {
-      if (j == i) continue;
-      const DNote &o = sm.notes[sm.note_perm[j]];
-      int c = second ? cmp_by_addr(sm, o, me) : cmp_by_attr(sm, o, me);
-      if (c < 0 || (c == 0 && j < i)) r++;
+// objcopy sorts the notes with libc qsort(); its first comparator is not antisymmetric for nested
+// ranges, so the result depends on the exact comparison sequence.  This image's glibc 2.39 qsort
+// is the classic top-down merge sort (msort.c: n1 = n / 2, sort both halves, merge taking the left
+// element while cmp(left, right) <= 0).  Restated here on the note permutation, run by one lane
+// (n <= 320: a few thousand comparisons).  `second` selects the comparator.
+__device__ void msort_notes(PlanSmem &sm, int n, bool second) {
+  struct Frame { uint16_t lo, n; uint8_t stage; };
+  Frame stack[12];
+  int sp = 0;
+  stack[sp++] = Frame{0, (uint16_t)n, 0};
+  while (sp > 0) {
+    Frame &f = stack[sp - 1];
+    if (f.n <= 1) { sp--; continue; }
+    const int n1 = f.n / 2, n2 = f.n - n1;
+    if (f.stage == 0) { f.stage = 1; stack[sp++] = Frame{f.lo, (uint16_t)n1, 0}; continue; }
+    if (f.stage == 1) { f.stage = 2; stack[sp++] = Frame{(uint16_t)(f.lo + n1), (uint16_t)n2, 0}; continue; }
+    int i = f.lo, j = f.lo + n1, k = 0, r1 = n1, r2 = n2;
+    while (r1 > 0 && r2 > 0) {
+      const DNote &a = sm.notes[sm.note_perm[i]], &b = sm.notes[sm.note_perm[j]];
+      const int c = second ? cmp_by_addr(sm, a, b) : cmp_by_attr(sm, a, b);
+      if (c <= 0) { sm.note_tmp[k++] = sm.note_perm[i++]; r1--; }
+      else { sm.note_tmp[k++] = sm.note_perm[j++]; r2--; }
     }
-    sm.note_tmp[r] = sm.note_perm[i];
+    while (r1 > 0) { sm.note_tmp[k++] = sm.note_perm[i++]; r1--; }
+    for (int q = 0; q < k; q++) sm.note_perm[f.lo + q] = sm.note_tmp[q];
+    sp--;
   }
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) sm.note_perm[i] = sm.note_tmp[i];
-  __syncwarp();
 }
 
 // Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
@@ -266,9 +272,8 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     return size;
   }
   const int n = s_n;
-  warp_sort_notes(sm, n, false, lane);
-  if (sm.note_tie) { *err = 3; return size; }  // name ties of unequal length: order is libc-specific
   if (lane == 0) {
+    msort_notes(sm, n, false);
     for (int i = 0; i < n; i++) {
       DNote &pn = sm.notes[sm.note_perm[i]];
       if (pn.type == 0) continue;
@@ -297,9 +302,8 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       }
     }
   }
-  __syncwarp();
-  warp_sort_notes(sm, n, true, lane);
   if (lane == 0) {
+    msort_notes(sm, n, true);
     uint32_t w = 0;
     uint64_t ps = 0, pe = 0;
     for (int i = 0; i < n; i++) {
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       int err = 0;
       uint8_t *dst = scr + SCR_NOTES + scr_used;
       uint32_t ns = merge_build_notes(sm, (uint32_t)h.sh_size, dst, &err, lane);
-      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? ST_PLANNER_LIMIT : err == 3 ? ST_UNSUPPORTED_LAYOUT : ST_BAD_NOTES); break; }
+      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES); break; }
       if (lane == 0) {
         sm.new_size[i] = ns;
         sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);

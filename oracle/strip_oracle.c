@@ -187,9 +187,25 @@ static int cmp_notes_by_addr(const void *a, const void *b) {
   return 0;
 }
 
-/* glibc 2.39 qsort is an in-place introsort; with comparators that return 0 for distinct
- * elements its output order depends on that exact algorithm.  We call the C library's qsort
- * ourselves, which is the same one /usr/bin/strip links against in this image. */
+/* objcopy sorts with libc qsort().  compare_gnu_build_notes is not antisymmetric for nested
+ * ranges ([0x1000,0x1400] and [0x1200,0x1300] each compare "less" than the other), so the outcome
+ * depends on the comparison sequence of the C library.  glibc 2.39 (this image; its qsort was
+ * probed stable for n up to 1.2e6) uses the classic top-down merge sort of stdlib/msort.c:
+ * n1 = n / 2, sort both halves, merge taking the left element while cmp(left, right) <= 0.
+ * Restated here so the oracle does not depend on which libc it is linked against. */
+static void msort_notes(BNote *b, size_t n, BNote *tmp, int (*cmp)(const void *, const void *)) {
+  if (n <= 1) return;
+  size_t n1 = n / 2, n2 = n - n1;
+  BNote *b1 = b, *b2 = b + n1, *t = tmp;
+  msort_notes(b1, n1, tmp, cmp);
+  msort_notes(b2, n2, tmp, cmp);
+  while (n1 > 0 && n2 > 0) {
+    if (cmp(b1, b2) <= 0) { *t++ = *b1++; n1--; }
+    else { *t++ = *b2++; n2--; }
+  }
+  if (n1 > 0) memcpy(t, b1, n1 * sizeof(BNote));
+  memcpy(b, tmp, (n - n2) * sizeof(BNote));
+}
 
 /* Returns new size (<= size) written into `out` (capacity 2*size); or `size` with out == copy. */
 static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out, int *err) {
@@ -251,7 +267,8 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
   if ((v1 && v2) || (v1 && v3) || (v2 && v3)) goto bad;
   if (v3 == 0) { free(notes); return size; } /* only v3 notes are merged */
 
-  qsort(notes, (size_t)(pend - notes), sizeof(BNote), cmp_notes_by_attr);
+  BNote *tmp = (BNote *)calloc((size_t)(pend - notes) + 1, sizeof(BNote));
+  msort_notes(notes, (size_t)(pend - notes), tmp, cmp_notes_by_attr);
 
   for (pn = notes; pn < pend; pn++) {
     if (note_is_deleted(pn)) continue;
@@ -282,7 +299,8 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
     }
   }
 
-  qsort(notes, (size_t)(pend - notes), sizeof(BNote), cmp_notes_by_addr);
+  msort_notes(notes, (size_t)(pend - notes), tmp, cmp_notes_by_addr);
+  free(tmp);
 
   uint8_t *w = out;
   uint64_t prev_start = 0, prev_end = 0;
