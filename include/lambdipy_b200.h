@@ -148,6 +148,11 @@ typedef struct lb2_fill_region {
 int lb2_corpus_fill(lb2_ctx *ctx, void *d_arena, const lb2_fill_region *h_regions, uint32_t n_regions,
                     uint64_t seed, void *stream);
 
+/* Copies n host-built blobs (ELF headers, notes, string tables) into the arena:
+ * arena[h_dst[i] .. +h_len[i]) = h_data[h_src[i] .. +h_len[i]).  Synchronous. */
+int lb2_corpus_scatter(lb2_ctx *ctx, void *d_arena, const void *h_data, uint64_t data_bytes, const uint64_t *h_dst,
+                       const uint64_t *h_src, const uint64_t *h_len, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ EXPORTS = [
     "lb2_dev_alloc", "lb2_dev_free", "lb2_pinned_alloc", "lb2_pinned_free",
     "lb2_memcpy_h2d", "lb2_memcpy_d2h", "lb2_memset_d",
     "lb2_strip_device_async", "lb2_batch_results", "lb2_strip_host", "lb2_strip_tree",
-    "lb2_plan_device", "lb2_corpus_fill",
+    "lb2_plan_device", "lb2_corpus_fill", "lb2_corpus_scatter",
 ]
 
 
@@ -116,6 +116,8 @@ def load():
     lib.lb2_plan_device.restype = C.c_int
     lib.lb2_corpus_fill.argtypes = [vp, vp, C.POINTER(FillRegion), C.c_uint32, C.c_uint64, vp]
     lib.lb2_corpus_fill.restype = C.c_int
+    lib.lb2_corpus_scatter.argtypes = [vp, vp, vp, C.c_uint64, u64p, u64p, u64p, C.c_uint32]
+    lib.lb2_corpus_scatter.restype = C.c_int
     _lib = lib
     return lib
 

@@ -611,4 +611,45 @@ int lb2_corpus_fill(lb2_ctx *ctx, void *d_arena, const lb2_fill_region *h_region
   return LB2_OK;
 }
 
+int lb2_corpus_scatter(lb2_ctx *ctx, void *d_arena, const void *h_data, uint64_t data_bytes, const uint64_t *h_dst,
+                       const uint64_t *h_src, const uint64_t *h_len, uint32_t n) {
+  if (!ctx || !d_arena || (n && (!h_data || !h_dst || !h_src || !h_len))) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  if (!n) return LB2_OK;
+  cudaStream_t s = ctx->stream;
+  uint8_t *d_stage = nullptr;
+  CK(cudaMalloc(&d_stage, data_bytes + 256));
+  CK(cudaMemcpyAsync(d_stage, h_data, data_bytes, cudaMemcpyHostToDevice, s));
+  std::vector<Tile> tiles;
+  for (uint32_t i = 0; i < n; i++)
+    for (uint64_t o = 0; o < h_len[i]; o += TILE_BYTES) {
+      Tile t;
+      t.src = reinterpret_cast<uint64_t>(d_stage) + h_src[i] + o;
+      t.dst_rel = h_dst[i] + o;
+      t.len = (uint32_t)std::min<uint64_t>(TILE_BYTES, h_len[i] - o);
+      t.file = 0;
+      tiles.push_back(t);
+    }
+  Tile *d_tiles = nullptr;
+  BatchCounters *d_ctr = nullptr;
+  uint64_t *d_off = nullptr;
+  CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(Tile)));
+  CK(cudaMalloc(&d_ctr, sizeof(BatchCounters)));
+  CK(cudaMalloc(&d_off, sizeof(uint64_t)));
+  BatchCounters c;
+  memset(&c, 0, sizeof c);
+  c.n_tiles = tiles.size();
+  uint64_t zero = 0;
+  CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_ctr, &c, sizeof c, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_off, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
+  CompactArgs ca;
+  ca.tiles = d_tiles; ca.ctr = d_ctr; ca.out_off = d_off; ca.out = static_cast<uint8_t *>(d_arena);
+  launch_compact(ca, ctx->sm_count * 4, s);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  cudaFree(d_stage); cudaFree(d_tiles); cudaFree(d_ctr); cudaFree(d_off);
+  return LB2_OK;
+}
+
 }  // extern "C"
