@@ -271,12 +271,8 @@ class Corpus:
             # keep the log-uniform shape, stop once the declared cap would be exceeded
             keep = np.cumsum(sizes) <= max_total
             sizes, fracs = sizes[keep], fracs[keep]
-        idx = np.arange(len(sizes))
-        # shard: sort by size descending, deal round-robin -- balanced and deterministic
-        order = np.argsort(-sizes, kind="stable")
-        mine = order[rank::world]
-        mine.sort()
-        self.global_index = idx[mine]
+        from .sharding import shard_indices
+        self.global_index = shard_indices(sizes, rank, world)  # size-sorted round-robin
         self.files = []
         for gi in self.global_index:
             frng = np.random.default_rng([self.seed, 11, int(gi)])

@@ -161,12 +161,12 @@ __device__ int cmp_by_attr(const PlanSmem &sm, const DNote &a, const DNote &b) {
 }
 // second sort: by address range (objcopy.c sort_gnu_build_notes)
 __device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
+  if (a.type == 0x100 && b.type != 0x100) return -1;  // OPEN notes first
+  if (a.type != 0x100 && b.type == 0x100) return 1;
   if (a.start < b.start) return -1;
   if (a.start > b.start) return 1;
-  if (a.end > b.end) return -1;
+  if (a.end > b.end) return -1;                        // larger ranges first
   if (a.end < b.end) return 1;
-  if (a.type == 0x100 && b.type != 0x100) return -1;
-  if (a.type != 0x100 && b.type == 0x100) return 1;
   bool v1 = note_is_version(sm, a), v2 = note_is_version(sm, b);
   if (v1 && !v2) return -1;
   if (!v1 && v2) return 1;
@@ -292,6 +292,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
         bool merge;
         if (back.end < pn.start) merge = (((back.end + 15) & ~15ull) < pn.start);
         else merge = (back.end != pn.end);
+        if (back.type != pn.type) merge = false;  // OPEN and FUNC notes are never combined
         if (merge) {
           if (pn.start < back.start) back.start = pn.start;
           if (pn.end > back.end) back.end = pn.end;

@@ -1,0 +1,93 @@
+"""Host-side mirror of the one reference entry point that contains the strip step.
+
+Reference: lambdipy.project_build.install_non_resolved_requirements
+(/root/reference/lambdipy/project_build.py:234-277).  That function writes a bash script into
+`<build_directory>/build` -- pip install of the unresolved requirements, removal of *.egg-info,
+*.dist-info, __pycache__ and tests directories, and, last, `find ... -name "*.so" | xargs strip`
+(:260) -- runs it on the host (:268) or in a lambci container (:274) and deletes it (:277).
+
+This mirror keeps the signature, the printed messages, the script (minus its last line) and the
+exit-code convention, and performs the strip with the B200 library on the build tree once the
+script has finished.  Nothing else of the reference is re-implemented here: requirement
+resolution, Docker builds, release download stay in the reference package (see patch.py).
+
+Backend switch (additive; the reference's TODO at cli.py:34-39 asks for one):
+    LAMBDIPY_STRIP_BACKEND=b200   default: CUDA path; raises if no B200 / library is present
+    LAMBDIPY_STRIP_BACKEND=gnu    the reference's own shell line, untouched
+    LAMBDIPY_STRIP_BACKEND=off    do not strip
+"""
+import os
+import stat
+import subprocess
+import sys
+
+XARGS_FAILURE_RC = 123  # what `find | xargs strip` returns when any strip invocation fails
+
+
+def _script_lines(install_dir, pip_args, keep_tests):
+    keep = "\\|".join(keep_tests) if keep_tests else "*"
+    pip_line = ("pip install %s -t %s" % (pip_args, install_dir)) if pip_args else ""
+    return [
+        "#!/bin/bash",
+        "set -ex",
+        pip_line,
+        "rm -rf %s/*.egg-info" % install_dir,
+        "rm -rf %s/*.dist-info" % install_dir,
+        "find %s/ -name __pycache__ | xargs rm -rf" % install_dir,
+        'find %s/ -name tests | grep -v "%s" | xargs rm -rf' % (install_dir, keep),
+    ]
+
+
+def _reference_strip_line(install_dir):
+    return 'find %s/ -name "*.so" | xargs strip' % install_dir  # project_build.py:260
+
+
+def strip_build_tree(build_directory, backend=None):
+    """The replacement for project_build.py:260.  Returns the process-style return code."""
+    backend = (backend or os.environ.get("LAMBDIPY_STRIP_BACKEND", "b200")).lower()
+    if backend == "off":
+        return 0
+    if backend == "gnu":
+        return subprocess.call(["bash", "-c", "set -o pipefail; " + _reference_strip_line(build_directory)])
+    if backend != "b200":
+        raise ValueError("LAMBDIPY_STRIP_BACKEND must be b200, gnu or off (got %r)" % backend)
+    from .strip import strip_tree  # raises ImportError / NoDeviceError: no silent CPU path
+    st = strip_tree(build_directory, suffix=".so", device=int(os.environ.get("LAMBDIPY_B200_DEVICE", "0")),
+                    fallback_host_strip=True)
+    print("Stripped %d shared objects on the GPU (%d via host strip), %.1f MB -> %.1f MB" %
+          (st["n_gpu"], st["n_fallback"], st["in_bytes"] / 1e6, st["out_bytes"] / 1e6))
+    return XARGS_FAILURE_RC if st["n_failed"] else 0
+
+
+def install_non_resolved_requirements(resolved_requirements, requirements, python_version, keep_tests=None, no_docker=False,
+                                      build_directory='./build'):
+    install_dir = build_directory if no_docker else '/tmp/export'
+    pending = [r['line'] for r in requirements if resolved_requirements[r['requirement'].name] is None]
+    pip_args = ''.join(' "%s"' % line for line in pending)
+    if pending:
+        print('Installing remaining packages via pip')
+
+    script_path = build_directory + '/build'
+    with open(script_path, 'w') as f:
+        f.write('\n'.join(_script_lines(install_dir, pip_args, keep_tests)) + '\n')
+    os.chmod(script_path, os.stat(script_path).st_mode | stat.S_IEXEC)
+    with open(script_path) as f:
+        print(f.read())
+
+    if no_docker:
+        print("Installing without docker...")
+        return_code = subprocess.Popen([script_path]).wait()
+        if return_code == 0:
+            return_code = strip_build_tree(build_directory)
+        if return_code != 0:
+            print("Error in building lambdipy build.")
+            sys.exit(return_code)
+    else:
+        print("Installing in a docker container...")
+        from lambdipy.project_build import _run_command_in_docker  # the reference's container runner, unchanged
+        _run_command_in_docker('%s/build' % install_dir, build_directory=build_directory, python_version=python_version)
+        # the container wrote into the bind-mounted host directory (reference :179-184, uid :219)
+        strip_build_tree(build_directory)
+
+    print('Finalizing the build')
+    os.remove(script_path)

@@ -176,12 +176,13 @@ static int cmp_notes_by_attr(const void *a, const void *b) {
 
 static int cmp_notes_by_addr(const void *a, const void *b) {
   const BNote *p1 = (const BNote *)a, *p2 = (const BNote *)b;
+  /* OPEN notes first, then by start address, larger ranges first (probe: random OPEN/FUNC mixes) */
+  if (note_is_open(p1) && !note_is_open(p2)) return -1;
+  if (!note_is_open(p1) && note_is_open(p2)) return 1;
   if (p1->start < p2->start) return -1;
   if (p1->start > p2->start) return 1;
   if (p1->end > p2->end) return -1;
   if (p1->end < p2->end) return 1;
-  if (note_is_open(p1) && !note_is_open(p2)) return -1;
-  if (!note_is_open(p1) && note_is_open(p2)) return 1;
   if (note_is_version(p1) && !note_is_version(p2)) return -1;
   if (!note_is_version(p1) && note_is_version(p2)) return 1;
   return 0;
@@ -288,6 +289,9 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
         int merge;
         if (back->end < pn->start) merge = (((back->end + 15) & ~(uint64_t)15) < pn->start);
         else merge = (back->end != pn->end);
+        /* only notes of the same kind are combined (probe: an OPEN and a FUNC note of the same
+         * attribute with overlapping ranges both survive; identical / contained ones do not) */
+        if (back->type != pn->type) merge = 0;
         if (merge) {
           back->start = back->start < pn->start ? back->start : pn->start;
           back->end = back->end > pn->end ? back->end : pn->end;

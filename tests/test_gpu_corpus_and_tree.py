@@ -1,0 +1,166 @@
+"""GPU tests at benchmark sizes and through the tree API.
+
+* synthetic corpus (BASELINE config 4): the device generator equals the host generator; a
+  stratified sample over the size deciles is bit-exact vs the oracle and GNU strip; at full size the
+  size-independent properties hold: outputs are well-formed ELF whose section table ends the file,
+  and strip is idempotent (second pass over the first pass's outputs reproduces them byte for byte).
+* lb2_strip_tree on a copy of the real wheels tree == the reference's shell line on another copy.
+"""
+import ctypes as C
+import os
+import random
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import elf_fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+
+def test_random_note_sections_gpu(gpu_ctx, oracle, variants, fixture_dir):
+    from lambdipy_b200 import strip as S
+    from test_oracle_vs_gnu_strip import _random_notes
+    rng = random.Random(77)
+    blobs = []
+    for case in range(60):
+        p = os.path.join(fixture_dir, "gpu_rnd_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([3, 8, 20, 60, 150])))
+        blobs.append(open(p, "rb").read())
+    outs, status, _ = S.strip_buffers(gpu_ctx, blobs)
+    for i, (b, o, st) in enumerate(zip(blobs, outs, status)):
+        rc, want = oracle.strip(b)
+        assert rc == 0 and st == 0 and o == want, "case %d" % i
+
+
+def test_synthetic_corpus_device_resident(gpu_ctx, oracle, tmp_path):
+    from lambdipy_b200.corpus import Corpus
+    from lambdipy_b200.device import DeviceBatch
+    corpus = Corpus(400, seed=0xB200)            # ~4.5 GB, sizes 1 KB .. 128 MB
+    batch = DeviceBatch.from_corpus(gpu_ctx, corpus)
+    try:
+        batch.strip_async()
+        st = batch.results()
+        assert st["n_ok"] == len(corpus) and st["n_unsupported"] == 0 and st["overflow"] == 0
+        assert st["in_bytes"] == corpus.total_bytes
+        assert st["out_bytes"] == int(batch.out_sizes.sum()) < st["in_bytes"]
+        # stratified sample over the size deciles vs oracle and the real binary
+        order = np.argsort(batch.sizes)
+        sample = sorted(set(int(order[min(len(order) - 1, (d * len(order)) // 10 + k)]) for d in range(10) for k in range(3)))
+        for i in sample:
+            data = batch.read_input(i)
+            assert data == corpus.materialize(i), "device generator != host generator (file %d)" % i
+            got = batch.read_output(i)
+            rc, want = oracle.strip(data)
+            assert rc == 0 and got == want, i
+            if len(data) < (32 << 20):
+                p = tmp_path / "s.so"
+                p.write_bytes(data)
+                gnu, err = F.gnu_strip_bytes(str(p), str(tmp_path))
+                assert gnu == got, (i, err)
+        # full-size structural property: section table ends the file, .shstrtab is last
+        out_host = np.empty(int(batch.out_off[-1]), dtype=np.uint8)
+        gpu_ctx.d2h(out_host.ctypes.data, batch.d_out, out_host.nbytes)
+        for i in range(len(corpus)):
+            o, n = int(batch.out_off[i]), int(batch.out_sizes[i])
+            hdr = out_host[o:o + 64].tobytes()
+            assert hdr[:4] == b"\x7fELF"
+            shoff, = struct.unpack_from("<Q", hdr, 0x28)
+            shnum, shstrndx = struct.unpack_from("<HH", hdr, 0x3c)
+            assert shoff + shnum * 64 == n and shstrndx == shnum - 1
+            assert not out_host[o + n:int(batch.out_off[i + 1])].any()  # padding between files untouched/zero
+        # idempotence at full size: second pass over the outputs
+        second = DeviceBatch(gpu_ctx, batch.out_off, batch.out_sizes[:len(corpus)])
+        try:
+            gpu_ctx.h2d(second.d_in, out_host.ctypes.data, out_host.nbytes)
+            second.strip_async()
+            st2 = second.results()
+            assert st2["n_ok"] == len(corpus)
+            assert (second.out_sizes[:len(corpus)] == batch.out_sizes[:len(corpus)]).all()
+            out2 = np.empty(int(second.out_off[-1]), dtype=np.uint8)
+            gpu_ctx.d2h(out2.ctypes.data, second.d_out, out2.nbytes)
+            assert out2.nbytes == out_host.nbytes and (out2 == out_host).all()
+        finally:
+            second.close()
+    finally:
+        batch.close()
+
+
+def test_output_capacity_error_is_reported(gpu_ctx, variants):
+    from lambdipy_b200 import _native as N
+    from lambdipy_b200.device import DeviceBatch
+    blobs = [open(variants[k], "rb").read() for k in sorted(variants)]
+    b = DeviceBatch.from_blobs(gpu_ctx, blobs)
+    try:
+        b.out_cap = 4096  # claim a tiny output arena
+        b.strip_async()
+        with pytest.raises(N.NativeError) as e:
+            b.results()
+        assert e.value.code == N.LB2_E_CAPACITY
+        b.out_cap = b.in_bytes + (16 << 20)
+        b.strip_async()
+        assert b.results()["n_ok"] == len(blobs)
+    finally:
+        b.close()
+
+
+def _copy_tree(dst):
+    sp = F.site_packages()
+    for r in ("numpy", "PIL", "numpy.libs", "pillow.libs", "sklearn", "scikit_learn.libs"):
+        shutil.copytree(os.path.join(sp, r), os.path.join(dst, r), symlinks=True,
+                        ignore=shutil.ignore_patterns("*.py", "*.pyc", "*.pyi", "__pycache__", "*.txt", "*.npy", "*.npz"))
+    os.symlink(os.path.join("numpy", "_core"), os.path.join(dst, "linkdir.so"))          # symlink named *.so: left alone
+    os.makedirs(os.path.join(dst, "dir.so"))                                               # directory named *.so: warning only
+    shutil.copy(os.path.join(sp, "numpy.libs", sorted(os.listdir(os.path.join(sp, "numpy.libs")))[0]), os.path.join(dst, "versioned.so.3"))
+
+
+def _snapshot(root):
+    out = {}
+    for d, dirs, fs in os.walk(root):
+        for f in fs:
+            p = os.path.join(d, f)
+            rel = os.path.relpath(p, root)
+            if os.path.islink(p):
+                out[rel] = ("link", os.readlink(p))
+            else:
+                with open(p, "rb") as fh:
+                    out[rel] = (os.stat(p).st_mode & 0o7777, fh.read())
+    return out
+
+
+def test_strip_tree_equals_reference_pipeline(gpu_ctx, tmp_path):
+    from lambdipy_b200 import strip as S
+    a, b = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    os.makedirs(a); os.makedirs(b)
+    _copy_tree(a); _copy_tree(b)
+    os.chmod(os.path.join(a, "versioned.so.3"), 0o640); os.chmod(os.path.join(b, "versioned.so.3"), 0o640)
+    rc = subprocess.run(["bash", "-c", 'find %s/ -name "*.so" | xargs strip' % a], capture_output=True)  # the reference's line
+    assert rc.returncode == 0, rc.stderr
+    st = S.strip_tree(b, ctx=gpu_ctx)
+    assert st["n_failed"] == 0 and st["n_fallback"] == 0 and st["n_gpu"] > 100
+    assert st["n_skipped"] >= 2                      # the symlink and the directory
+    sa, sb = _snapshot(a), _snapshot(b)
+    assert set(sa) == set(sb)
+    diff = [k for k in sa if sa[k] != sb[k]]
+    assert not diff, diff[:5]
+    assert not [f for f in os.listdir(os.path.join(b, "numpy.libs")) if ".lb2" in f]  # no temp files left behind
+
+
+def test_strip_tree_failure_and_tolerance(gpu_ctx, variants, tmp_path):
+    from lambdipy_b200 import strip as S
+    root = str(tmp_path / "t")
+    os.makedirs(root)
+    shutil.copy(variants["c_g"], os.path.join(root, "good.so"))
+    with open(os.path.join(root, "bogus.so"), "w") as f:
+        f.write("not an elf")
+    st = S.strip_tree(root, ctx=gpu_ctx)
+    assert st["n_gpu"] == 1 and st["n_failed"] == 1          # the reference's script would exit 123 here too
+    st = S.strip_tree(root, ctx=gpu_ctx, tolerate_non_elf=True)
+    assert st["n_failed"] == 0 and st["n_skipped"] == 1
+    empty = str(tmp_path / "empty")
+    os.makedirs(empty)
+    st = S.strip_tree(empty, ctx=gpu_ctx)
+    assert st["n_selected"] == 0 and st["n_failed"] == 0     # documented deviation: xargs would run `strip` with no args (rc 123)
