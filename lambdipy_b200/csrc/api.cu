@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include <climits>
 #include <dirent.h>
 #include <fcntl.h>
 #include <spawn.h>
@@ -427,30 +428,50 @@ static bool ends_with(const char *s, const char *suf) {
   return a >= b && memcmp(s + a - b, suf, b) == 0;
 }
 
-struct TreeFile { std::string path; uint64_t size; mode_t mode; };
+struct TreeFile { std::string path; uint64_t size; mode_t mode; uint32_t times; };
 
+// `find ROOT/ -name "*SUFFIX"`: every directory entry whose basename matches, of any type; find does
+// not descend into symlinked directories.  What `strip` then does with each path decides the rest:
+//   regular file           -> stripped in place
+//   symlink to a file      -> the TARGET is rewritten, the link stays (so libfoo.so -> libfoo.so.1
+//                             strips libfoo.so.1 even though that name does not match)
+//   directory / dangling   -> strip fails -> xargs exits 123 -> the reference's script aborts
+// A file reached through k matching paths is stripped k times by the reference; `times` keeps k.
 static void walk(const std::string &dir, const char *suffix, std::vector<TreeFile> &files, lb2_tree_stats *st) {
   DIR *d = opendir(dir.c_str());
   if (!d) return;
   while (dirent *e = readdir(d)) {
     if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
     std::string p = dir + "/" + e->d_name;
-    struct stat sb;
-    if (lstat(p.c_str(), &sb) != 0) continue;
-    const bool match = ends_with(e->d_name, suffix);  // find -name "*.so": basename test, any file type
-    if (match) st->n_selected++;
-    if (S_ISDIR(sb.st_mode)) {
-      if (match) st->n_skipped++;  // strip: "Warning: ... is a directory"
-      walk(p, suffix, files, st);
-    } else if (S_ISLNK(sb.st_mode)) {
-      if (match) st->n_skipped++;  // strip leaves a symlink named *.so a symlink
-    } else if (S_ISREG(sb.st_mode) && match) {
-      files.push_back({p, (uint64_t)sb.st_size, sb.st_mode});
-    } else if (match) {
-      st->n_skipped++;
+    struct stat lsb, sb;
+    if (lstat(p.c_str(), &lsb) != 0) continue;
+    const bool match = ends_with(e->d_name, suffix);
+    if (match) {
+      st->n_selected++;
+      if (stat(p.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        st->n_failed++;  // directory, dangling link, device ...: strip errors out
+      } else {
+        char real[PATH_MAX];
+        if (!realpath(p.c_str(), real)) st->n_failed++;
+        else {
+          if (S_ISLNK(lsb.st_mode)) st->n_skipped++;  // the link itself is left alone
+          files.push_back({real, (uint64_t)sb.st_size, sb.st_mode, 1});
+        }
+      }
     }
+    if (S_ISDIR(lsb.st_mode)) walk(p, suffix, files, st);
   }
   closedir(d);
+}
+
+static void dedupe(std::vector<TreeFile> &files) {
+  std::sort(files.begin(), files.end(), [](const TreeFile &a, const TreeFile &b) { return a.path < b.path; });
+  size_t w = 0;
+  for (size_t i = 0; i < files.size(); i++) {
+    if (w && files[w - 1].path == files[i].path) files[w - 1].times++;
+    else files[w++] = files[i];
+  }
+  files.resize(w);
 }
 
 static bool read_file(const std::string &p, uint8_t *dst, uint64_t n) {
@@ -519,6 +540,7 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
   std::string r = root;
   while (r.size() > 1 && r.back() == '/') r.pop_back();
   walk(r, suffix, files, &st);
+  dedupe(files);
   const uint32_t n = (uint32_t)files.size();
   std::vector<uint64_t> off(n + 1), sizes(n), out_off(n + 1), out_sizes(n);
   std::vector<int32_t> status(n);
@@ -550,6 +572,37 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
   int rc = LB2_OK;
   if (n) rc = lb2_strip_host(ctx, ctx->h_tree_in, off.data(), sizes.data(), n, ctx->h_tree_out, ctx->cap_tree_out, out_off.data(),
                              out_sizes.data(), status.data(), flags & 0xffu, &st.batch);
+  // files the reference would strip more than once (reached through several matching names):
+  // run the extra passes on the previous pass's output (strip is not always idempotent)
+  for (uint32_t pass = 1; rc == LB2_OK; pass++) {
+    std::vector<uint32_t> again;
+    for (uint32_t i = 0; i < n; i++) if (files[i].times > pass && status[i] == LB2_ST_OK) again.push_back(i);
+    if (again.empty()) break;
+    const uint32_t m = (uint32_t)again.size();
+    std::vector<uint64_t> off2(m + 1), sz2(m), ooff2(m + 1), osz2(m);
+    std::vector<int32_t> st2(m);
+    uint64_t p2 = 0;
+    for (uint32_t k = 0; k < m; k++) { off2[k] = p2; sz2[k] = out_sizes[again[k]]; p2 += (sz2[k] + 255) & ~255ull; }
+    off2[m] = p2;
+    // previous outputs become inputs (the input arena is free to reuse: it is at least as large)
+    for (uint32_t k = 0; k < m; k++) memcpy(ctx->h_tree_in + off2[k], ctx->h_tree_out + out_off[again[k]], sz2[k]);
+    std::vector<uint8_t> keep_out;  // outputs of files not in this pass stay where they are; new ones go to a scratch arena
+    uint8_t *h_tmp = nullptr;
+    const uint64_t cap2 = p2 + (uint64_t)m * 4096 + (16u << 20);
+    CK(cudaHostAlloc(&h_tmp, cap2, cudaHostAllocDefault));
+    lb2_stats b2;
+    rc = lb2_strip_host(ctx, ctx->h_tree_in, off2.data(), sz2.data(), m, h_tmp, cap2, ooff2.data(), osz2.data(), st2.data(), flags & 0xffu, &b2);
+    if (rc == LB2_OK) {
+      for (uint32_t k = 0; k < m; k++) {
+        const uint32_t i = again[k];
+        if (st2[k] != LB2_ST_OK) { status[i] = st2[k]; continue; }
+        // a re-stripped file never grows beyond its 256-byte-rounded slot by more than the slack between files
+        if (osz2[k] <= ((out_sizes[i] + 255) & ~255ull)) { memcpy(ctx->h_tree_out + out_off[i], h_tmp + ooff2[k], osz2[k]); out_sizes[i] = osz2[k]; }
+        else status[i] = LB2_ST_UNSUPPORTED_LAYOUT;  // hand to the host strip
+      }
+    }
+    cudaFreeHost(h_tmp);
+  }
   st.gpu_s = now_s() - t0;
   if (rc) { if (st_out) *st_out = st; return rc; }
 
@@ -578,13 +631,15 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
     if (non_elf && (flags & LB2_TREE_TOLERATE_NON_ELF)) { n_skipped++; return; }
     if ((flags & LB2_TREE_FALLBACK_HOST_STRIP) && !(flags & LB2_TREE_DRY_RUN)) {
       // the reference's own tool decides (and fails the build exactly when the reference would)
-      if (host_strip(files[i].path) == 0) n_fb++; else n_failed++;
+      bool ok = true;
+      for (uint32_t k = 0; k < files[i].times && ok; k++) ok = host_strip(files[i].path) == 0;
+      if (ok) n_fb++; else n_failed++;
     } else {
       n_failed++;
     }
   });
   st.fallback_s = now_s() - t0;
-  st.n_gpu = n_gpu; st.n_fallback = n_fb; st.n_failed = n_failed; st.n_skipped += n_skipped;
+  st.n_gpu = n_gpu; st.n_fallback = n_fb; st.n_failed += n_failed; st.n_skipped += n_skipped;
   st.in_bytes = in_b; st.out_bytes = out_b;
   if (st_out) *st_out = st;
   return LB2_OK;
