@@ -195,6 +195,7 @@ def workload_config(a, world):
 
 
 def run_b200(a, rank, local_rank, world):
+    os.environ["NCCL_DEBUG"] = os.environ.get("LB2_NCCL_DEBUG", "WARN")  # keep NCCL banners off stdout (one JSON line)
     import numpy as np
     import torch
     from lambdipy_b200 import _native as N
@@ -334,7 +335,7 @@ def run_b200(a, rank, local_rank, world):
             "dtype": "u8", "data": "synthetic", "config": workload_config(a, world),
             "totals": {"files": int(n_ok), "unsupported_files": int(n_uns), "in_gb": tot_in / 1e9, "out_gb": tot_out / 1e9,
                        "copied_gb": tot_copy / 1e9, "header_gb": tot_hdr / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "lb2_compact_tma_kernel" if os.environ.get("LB2_COMPACT_TMA") == "1" else "lb2_compact_kernel",
+            "roofline": {"bound": "hbm", "kernel": "lb2_compact_kernel" if os.environ.get("LB2_COMPACT_TMA") == "0" else "lb2_compact_tma_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": sum(compact_ms) / len(compact_ms),

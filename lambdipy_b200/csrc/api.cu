@@ -55,7 +55,7 @@ struct lb2_ctx {
   Workspace ws;               // lb2_strip_device_async / lb2_plan_device
   std::string err;
   int compact_ctas_per_sm = 4;
-  int use_tma = 0;
+  int use_tma = 1;             // bulk-copy engine kernel (0.97 of copy peak) ; LB2_COMPACT_TMA=0 selects the LSU kernel (0.90)
   // host pipeline slots
   struct Slot {
     Workspace ws;

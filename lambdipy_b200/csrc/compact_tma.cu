@@ -76,43 +76,53 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) lb2_compact_tma_kernel(Compact
   }
   __syncthreads();
 
-  if (warp == 0) {
-    // ---- producer: one lane queues bulk loads, running up to TMA_STAGES tiles ahead
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  // Producer and storer warps read tile descriptors 32 at a time (one per lane, one round trip to L2
+  // for the whole batch) and hand them to their issuing lane by shuffle: a per-tile dependent load
+  // in front of every 16 KB bulk copy would cap an SM at one tile per L2 latency.
+  if (warp == 0 || warp == 1) {
+    uint32_t it = 0;
+    for (unsigned long long tb = blockIdx.x; tb < n_tiles; tb += (unsigned long long)gridDim.x * 32) {
+      const unsigned long long t = tb + (unsigned long long)lane * gridDim.x;
+      uint64_t src = 0, dst = 0;
+      uint32_t body = 0;
+      if (t < n_tiles) {
         const TileView v = load_tile(a, t);
         const BulkSplit sp = bulk_split(v);
-        if (!sp.body) continue;
-        const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
-        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        mbar_expect_tx(&full_bar[s], sp.body);
-        bulk_g2s(smem + (size_t)s * TILE_BYTES, v.src + sp.head, sp.body, &full_bar[s]);
-        it++;
+        body = sp.body;
+        src = reinterpret_cast<uint64_t>(v.src) + sp.head;
+        dst = reinterpret_cast<uint64_t>(v.dst) + sp.head;
       }
-    }
-  } else if (warp == 1) {
-    // ---- storer: as each stage lands, queue its bulk store; release stages whose store has
-    //      finished reading shared memory
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const TileView v = load_tile(a, t);
-        const BulkSplit sp = bulk_split(v);
-        if (!sp.body) continue;
-        const uint32_t s = it % TMA_STAGES, round = it / TMA_STAGES;
-        mbar_wait(&full_bar[s], round & 1);
-        bulk_s2g(v.dst + sp.head, smem + (size_t)s * TILE_BYTES, sp.body);
-        bulk_commit();
-        if (it >= (uint32_t)TMA_STORES_IN_FLIGHT) {
-          bulk_wait_read<TMA_STORES_IN_FLIGHT>();
-          mbar_arrive(&empty_bar[(it - TMA_STORES_IN_FLIGHT) % TMA_STAGES]);
+      unsigned todo = __ballot_sync(0xffffffffu, body != 0);
+      while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t s_ = __shfl_sync(0xffffffffu, src, l), d_ = __shfl_sync(0xffffffffu, dst, l);
+        const uint32_t b_ = __shfl_sync(0xffffffffu, body, l);
+        if (lane == 0) {
+          const uint32_t st = it % TMA_STAGES, round = it / TMA_STAGES;
+          if (warp == 0) {
+            // ---- producer: queue the bulk load, running up to TMA_STAGES tiles ahead of the stores
+            if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
+            mbar_expect_tx(&full_bar[st], b_);
+            bulk_g2s(smem + (size_t)st * TILE_BYTES, reinterpret_cast<const void *>(s_), b_, &full_bar[st]);
+          } else {
+            // ---- storer: as the stage lands queue its bulk store; release the stage whose store
+            //      has finished reading shared memory
+            mbar_wait(&full_bar[st], round & 1);
+            bulk_s2g(reinterpret_cast<void *>(d_), smem + (size_t)st * TILE_BYTES, b_);
+            bulk_commit();
+            if (it >= (uint32_t)TMA_STORES_IN_FLIGHT) {
+              bulk_wait_read<TMA_STORES_IN_FLIGHT>();
+              mbar_arrive(&empty_bar[(it - TMA_STORES_IN_FLIGHT) % TMA_STAGES]);
+            }
+          }
         }
         it++;
       }
+    }
+    if (warp == 1 && lane == 0) {
       bulk_wait_read<0>();
-      // (no one waits on the remaining empty barriers)
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores globally performed before exit
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores performed before the CTA exits
     }
   } else {
     // ---- helpers: heads/tails of engine tiles, and every tile the engine does not take

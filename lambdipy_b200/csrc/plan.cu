@@ -19,6 +19,13 @@ struct DNote {
   uint16_t namesz;
 };
 
+template <int NB, int NN> struct NoteSmem {
+  DNote notes[NN];
+  uint16_t perm[NN], tmp[NN];
+  __align__(16) uint8_t buf[NB];
+};
+constexpr int32_t ST_RETRY_BIG_NOTES = 100;  // internal: small-variant verdict, never leaves the device
+
 struct PlanSmem {
   Ehdr eh;
   Shdr sh[MAX_SH];
@@ -41,11 +48,19 @@ struct PlanSmem {
   uint8_t order[MAX_SH + 1];
   uint8_t pkeep[MAX_PH];
   uint8_t piece[MAX_SH];
+  uint16_t name_len[MAX_SH];     // strlen of each section's name          (lane-parallel, phase C)
+  uint32_t name_hash[MAX_SH];    // FNV-1a of each section's name: cheap inequality test
+  uint64_t seg_mask[MAX_PH];     // kept sections carried by PT_LOAD j     (phase F)
+  uint64_t seg_bits[MAX_PH];     // ... of which have file contents (not NOBITS)
   char names[MAX_STR + 16];
-  DNote notes[MAX_NOTES];
-  uint16_t note_perm[MAX_NOTES];
-  uint16_t note_tmp[MAX_NOTES];
-  uint8_t note_buf[MAX_NOTE_BYTES];
+  // build-attribute note workspace: lives in a second shared array whose size is a template
+  // parameter of the kernel (small for the common case so that more files fit per SM; files with
+  // bigger note sections are redone by the large variant)
+  DNote *notes;
+  uint16_t *note_perm;
+  uint16_t *note_tmp;
+  uint8_t *note_buf;
+  int note_cap_bytes, note_cap_n;
   // scalars shared by the warp
   int fail;
   int nk, nent, n_ext, new_phnum, note_tie;
@@ -64,6 +79,14 @@ __device__ __forceinline__ bool d_streq(const char *a, const char *b) {
 __device__ __forceinline__ bool d_prefix(const char *s, const char *p) {
   for (int i = 0; p[i]; i++) if (s[i] != p[i]) return false;
   return true;
+}
+
+__device__ __forceinline__ uint32_t d_hash(const char *s, int *len_out) {
+  uint32_t h = 2166136261u;
+  int n = 0;
+  for (; s[n]; n++) h = (h ^ (uint8_t)s[n]) * 16777619u;
+  *len_out = n;
+  return h;
 }
 
 // Warp-cooperative global->shared copy.  16-byte vector loads when both sides allow it (the
@@ -214,7 +237,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     unsigned v1 = 0, v2 = 0, v3 = 0;
     uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
     while (remain >= 12) {
-      if (n >= MAX_NOTES) { s_err = 2; break; }
+      if (n >= sm.note_cap_n) { s_err = 2; break; }
       const uint8_t *h = sm.note_buf + p;
       uint32_t namesz = rd32(h), descsz = rd32(h + 4), type = rd32(h + 8);
       uint32_t padded = (namesz + 3) & ~3u;
@@ -338,11 +361,18 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
 
 #define LB2_FAIL(code) do { sm.fail = (code); } while (0)
 
+template <int NB, int NN, bool RETRY_PASS>
 __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __shared__ PlanSmem sm;
+  __shared__ NoteSmem<NB, NN> ns;
   const int lane = threadIdx.x;
   const uint32_t f = blockIdx.x;
   if (f >= a.n_files) return;
+  if (RETRY_PASS && a.status[f] != ST_RETRY_BIG_NOTES) return;
+  if (lane == 0) {
+    sm.notes = ns.notes; sm.note_perm = ns.perm; sm.note_tmp = ns.tmp; sm.note_buf = ns.buf;
+    sm.note_cap_bytes = NB; sm.note_cap_n = NN;
+  }
   const uint64_t base = a.in_off[f];
   const uint64_t n = a.in_size[f];
   const uint8_t *in = a.in + base;
@@ -400,6 +430,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       sm.src_addr[i] = reinterpret_cast<uint64_t>(in) + h.sh_offset;
       if (h.sh_name >= strsz) { err_mal = 1; continue; }
       if (h.sh_type != SHT_NOBITS && h.sh_type != SHT_NULL && (h.sh_offset > n || h.sh_size > n - h.sh_offset)) { err_mal = 1; continue; }
+      { int ln; sm.name_hash[i] = d_hash(sm.names + h.sh_name, &ln); sm.name_len[i] = (uint16_t)ln; }
       if (i == 0) { sm.keep[0] = 1; continue; }
       const char *nm = sm.names + h.sh_name;
       const bool alloc = (h.sh_flags & SHF_ALLOC) != 0;
@@ -452,13 +483,16 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       const Shdr &h = sm.sh[i];
       if (!sm.keep[i] || h.sh_type != SHT_NOTE || (h.sh_flags & SHF_ALLOC)) continue;
       if (!d_prefix(sm.names + h.sh_name, ".gnu.build.attributes")) continue;
-      if (h.sh_size > MAX_NOTE_BYTES || scr_used + h.sh_size > MAX_NOTE_BYTES) { if (lane == 0) LB2_FAIL(ST_PLANNER_LIMIT); break; }
+      if (h.sh_size > (uint64_t)NB || scr_used + h.sh_size > MAX_NOTE_BYTES) {
+        if (lane == 0) LB2_FAIL((!RETRY_PASS && h.sh_size <= MAX_NOTE_BYTES && scr_used + h.sh_size <= MAX_NOTE_BYTES) ? ST_RETRY_BIG_NOTES : ST_PLANNER_LIMIT);
+        break;
+      }
       warp_g2s(sm.note_buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
       __syncwarp();
       int err = 0;
       uint8_t *dst = scr + SCR_NOTES + scr_used;
       uint32_t ns = merge_build_notes(sm, (uint32_t)h.sh_size, dst, &err, lane);
-      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES); break; }
+      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? (RETRY_PASS ? ST_PLANNER_LIMIT : ST_RETRY_BIG_NOTES) : ST_BAD_NOTES); break; }
       if (lane == 0) {
         sm.new_size[i] = ns;
         sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
@@ -469,7 +503,10 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     }
   }
   __syncwarp();
-  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  if (sm.fail) {
+    if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; if (sm.fail != ST_RETRY_BIG_NOTES) atomicAdd(&a.ctr->n_unsupported, 1u); }
+    return;
+  }
 
   // ---- F. which PT_LOAD carries each kept alloc section (lane-parallel), which phdrs survive (R11)
   {
@@ -488,11 +525,13 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   {
     int keepj = 1;
     if (lane < phnum) {
-      if (sm.ph[lane].p_type == PT_LOAD && sm.ph[lane].p_offset != 0) {
-        int members = 0;
-        for (int i = 1; i < shnum; i++) members += (sm.keep[i] && sm.seg[i] == lane);
-        if (!members) keepj = 0;
-      }
+      uint64_t mm = 0, mb = 0;
+      if (sm.ph[lane].p_type == PT_LOAD)
+        for (int i = 1; i < shnum; i++)
+          if (sm.keep[i] && sm.seg[i] == lane) { mm |= 1ull << i; if (sm.sh[i].sh_type != SHT_NOBITS) mb |= 1ull << i; }
+      sm.seg_mask[lane] = mm;
+      sm.seg_bits[lane] = mb;
+      if (sm.ph[lane].p_type == PT_LOAD && sm.ph[lane].p_offset != 0 && !mm) keepj = 0;
       sm.pkeep[lane] = (uint8_t)keepj;
       sm.nph[lane] = sm.ph[lane];
     }
@@ -511,15 +550,14 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       if (p.p_vaddr < last_vaddr) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); break; }
       last_vaddr = p.p_vaddr;
       const bool first = (p.p_offset == 0);
-      bool contents = false;
-      for (int i = 1; i < shnum; i++) if (sm.keep[i] && sm.seg[i] == j && sm.sh[i].sh_type != SHT_NOBITS) contents = true;
+      const bool contents = sm.seg_bits[j] != 0;
       uint64_t new_off = 0;
       if (!first) { uint64_t al = p.p_align ? p.p_align : 1; new_off = cur + ((p.p_vaddr - cur) % al); }
       uint64_t off = first ? cur : new_off;
       uint64_t mem_end = p.p_vaddr + (first ? cur : 0), file_end = off;
       int idx = 0;
-      for (int i = 1; i < shnum; i++) {
-        if (!sm.keep[i] || sm.seg[i] != j) continue;
+      for (uint64_t mm = sm.seg_mask[j]; mm; mm &= mm - 1) {  // members in ascending section index
+        const int i = __ffsll((long long)mm) - 1;
         const Shdr &h = sm.sh[i];
         uint64_t want = new_off + (h.sh_addr - p.p_vaddr);
         if (h.sh_type != SHT_NOBITS) {
@@ -577,14 +615,14 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
           const uint64_t start = sm.sh[first].sh_addr, end = start + p.p_memsz;
           for (int l = 0; l < phnum && !ok; l++) {
             if (sm.ph[l].p_type != PT_LOAD || !sm.pkeep[l]) continue;
-            int lf = -1, ll = -1;
-            for (int i = 1; i < shnum; i++) if (sm.keep[i] && sm.seg[i] == l) { if (lf < 0) lf = i; ll = i; }
-            if (lf < 0) continue;
+            const uint64_t lm = sm.seg_mask[l];
+            if (!lm) continue;
+            const int lf = __ffsll((long long)lm) - 1, ll = 63 - __clzll((long long)lm);
             const Shdr &hl = sm.sh[ll];
             uint64_t lend = hl.sh_addr + ((hl.sh_type == SHT_NOBITS && (hl.sh_flags & SHF_TLS)) ? 0 : hl.sh_size);
             if (!(lend > start && sm.sh[lf].sh_addr < end)) continue;
-            for (int i = 1; i < shnum; i++) {
-              if (!sm.keep[i] || sm.seg[i] != l) continue;
+            for (uint64_t mm = lm; mm; mm &= mm - 1) {
+              const int i = __ffsll((long long)mm) - 1;
               const Shdr &h = sm.sh[i];
               if (h.sh_addr >= start && h.sh_addr < end && h.sh_size != 0) {
                 q.p_vaddr = h.sh_addr;
@@ -643,8 +681,12 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     const int i = sm.order[k];
     const char *nm = sm.names + sm.sh[i].sh_name;
     int first = k;
-    if (d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
-    else for (int q = 1; q < k; q++) if (d_streq(nm, sm.names + sm.sh[sm.order[q]].sh_name)) { first = q; break; }
+    const uint32_t hh = sm.name_hash[i];
+    if (sm.name_len[i] == 9 && d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
+    else for (int q = 1; q < k; q++) {
+      const int oi = sm.order[q];
+      if (sm.name_hash[oi] == hh && sm.name_len[oi] == sm.name_len[i] && d_streq(nm, sm.names + sm.sh[oi].sh_name)) { first = q; break; }
+    }
     sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
   }
   __syncwarp();
@@ -653,12 +695,12 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; nent = 1;
     for (int k = 1; k < nk; k++) {
       const int i = sm.order[k];
-      if (sm.piece[k] == k && sm.names[sm.sh[i].sh_name] != 0) {
+      if (sm.piece[k] == k && sm.name_len[i] != 0) {
         sm.ent_str[nent] = (uint16_t)sm.sh[i].sh_name;
-        sm.ent_len[nent] = (uint16_t)d_strlen(sm.names + sm.sh[i].sh_name);
+        sm.ent_len[nent] = sm.name_len[i];
         sm.sec_ent[i] = (uint8_t)nent;
         nent++;
-      } else if (sm.names[sm.sh[i].sh_name] == 0) {
+      } else if (sm.name_len[i] == 0) {
         sm.sec_ent[i] = 0xff;  // empty name -> sh_name 0
       } else {
         sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
@@ -736,11 +778,20 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
         else if (d_prefix(nm, ".rel")) t = nm + 4;
         int target = -1;
         if (t && *t) {
+          auto find_name = [&](const char *want) {
+            int wl;
+            const uint32_t wh = d_hash(want, &wl);
+            for (int q = 1; q < nk; q++) {
+              const int oi = sm.order[q];
+              if (sm.name_hash[oi] == wh && sm.name_len[oi] == wl && d_streq(sm.names + sm.sh[oi].sh_name, want)) return q;
+            }
+            return -1;
+          };
           if (d_streq(t, ".plt")) {
-            for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, ".got.plt")) { target = q; break; }
-            if (target < 0) for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, ".got")) { target = q; break; }
+            target = find_name(".got.plt");
+            if (target < 0) target = find_name(".got");
           } else {
-            for (int q = 1; q < nk; q++) if (d_streq(sm.names + sm.sh[sm.order[q]].sh_name, t)) { target = q; break; }
+            target = find_name(t);
           }
         }
         if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
@@ -896,7 +947,11 @@ __global__ void __launch_bounds__(1024) lb2_scan_kernel(const uint64_t *out_size
 }
 
 void launch_plan(const PlanArgs &a, cudaStream_t s) {
-  if (a.n_files) lb2_plan_kernel<<<a.n_files, 32, 0, s>>>(a);
+  if (!a.n_files) return;
+  // common case: <= 1 KB / 52 notes of build attributes per section -> ~19 KB smem, 11 files per SM
+  lb2_plan_kernel<1024, 52, false><<<a.n_files, 32, 0, s>>>(a);
+  // files with larger note sections (annobin-built wheels): full-size workspace, everyone else exits at once
+  lb2_plan_kernel<MAX_NOTE_BYTES, MAX_NOTES, true><<<a.n_files, 32, 0, s>>>(a);
 }
 void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, cudaStream_t s) {
   lb2_scan_kernel<<<1, 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr);
