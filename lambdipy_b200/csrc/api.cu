@@ -267,7 +267,7 @@ void *lb2_dev_alloc(lb2_ctx *ctx, uint64_t bytes) {
 void lb2_dev_free(lb2_ctx *, void *p) { if (p) cudaFree(p); }
 void *lb2_pinned_alloc(lb2_ctx *ctx, uint64_t bytes) {
   void *p = nullptr;
-  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 256, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 256, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) { if (ctx) ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return nullptr; }
   return p;
 }
@@ -313,6 +313,29 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, c
   CK(cudaSetDevice(ctx->device));
   const uint8_t *h_in = static_cast<const uint8_t *>(h_in_v);
   uint8_t *h_out = static_cast<uint8_t *>(h_out_v);
+  // Zero-copy path: when both arenas are pinned and mapped into the device address space the
+  // kernels work on them directly over PCIe -- the plan kernel pulls only headers, the compaction
+  // kernel pulls only the KEPT extents and pushes the stripped files straight into host memory.
+  // Dropped sections (.symtab/.strtab/.debug_*) never cross the bus, uploads and downloads run
+  // concurrently in both directions, and nothing has to fit in HBM.
+  if (env_u64("LB2_HOST_ZEROCOPY", 1) && n_files) {
+    void *d_in_alias = nullptr, *d_out_alias = nullptr;
+    cudaPointerAttributes ai, ao;
+    const bool ok = cudaPointerGetAttributes(&ai, h_in) == cudaSuccess && ai.type == cudaMemoryTypeHost &&
+                    cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ao.type == cudaMemoryTypeHost &&
+                    cudaHostGetDevicePointer(&d_in_alias, const_cast<uint8_t *>(h_in), 0) == cudaSuccess &&
+                    cudaHostGetDevicePointer(&d_out_alias, h_out, 0) == cudaSuccess;
+    cudaGetLastError();  // clear "invalid value" from probing pageable memory
+    if (ok) {
+      int rc = enqueue_batch(ctx, ctx->ws, static_cast<const uint8_t *>(d_in_alias), h_in_off, h_in_sizes, n_files,
+                             static_cast<uint8_t *>(d_out_alias), out_capacity, flags, ctx->stream, true);
+      if (rc) return rc;
+      lb2_stats st;
+      rc = collect_batch(ctx, ctx->ws, h_out_off, h_out_sizes, h_status, &st);
+      if (stats) *stats = st;
+      return rc;
+    }
+  }
   const uint64_t chunk_bytes = env_u64("LB2_CHUNK_MB", 256) << 20;
   lb2_stats total;
   memset(&total, 0, sizeof total);

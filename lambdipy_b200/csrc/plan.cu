@@ -14,9 +14,13 @@ namespace lb2 {
 
 struct DNote {
   uint64_t start, end;
+  uint64_t key;     // bytes 3..10 of the name, big-endian packed, zero padded: decides most name comparisons
   uint32_t type;
   uint16_t off;     // offset of the note header inside note_buf
   uint16_t namesz;
+  uint16_t cls;     // index of the first note with the identical name (equality class)
+  uint8_t ver;      // is a "GA$<version>" note
+  uint8_t pad;
 };
 
 template <int NB, int NN> struct NoteSmem {
@@ -162,17 +166,25 @@ __device__ __forceinline__ uint64_t rd64(const uint8_t *p) { return (uint64_t)rd
 __device__ __forceinline__ void wr32(uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; }
 __device__ __forceinline__ void wr64(uint8_t *p, uint64_t v) { wr32(p, (uint32_t)v); wr32(p + 4, (uint32_t)(v >> 32)); }
 
-__device__ __forceinline__ bool note_is_version(const PlanSmem &sm, const DNote &n) {
-  const uint8_t *nm = sm.note_buf + n.off + 12;
-  return n.namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1;
+// memcmp(name1 + 3, name2 + 3, min(namesz) - 3) of objcopy's compare_gnu_build_notes, answered from
+// the precomputed equality class and 8-byte key whenever they decide it
+__device__ __forceinline__ int cmp_note_names(const PlanSmem &sm, const DNote &a, const DNote &b) {
+  if (a.cls == b.cls) return 0;
+  const int m = (int)(a.namesz < b.namesz ? a.namesz : b.namesz) - 3;
+  if (m <= 0) return 0;
+  if (m >= 8) {
+    if (a.key != b.key) return a.key < b.key ? -1 : 1;
+    const uint8_t *n1 = sm.note_buf + a.off + 12 + 3, *n2 = sm.note_buf + b.off + 12 + 3;
+    for (int i = 8; i < m; i++) if (n1[i] != n2[i]) return (int)n1[i] - (int)n2[i];
+    return 0;
+  }
+  const uint64_t x = a.key >> (8 * (8 - m)), y = b.key >> (8 * (8 - m));
+  return x == y ? 0 : (x < y ? -1 : 1);
 }
-
 // first sort: by attribute name, then by range (objcopy.c compare_gnu_build_notes)
 __device__ int cmp_by_attr(const PlanSmem &sm, const DNote &a, const DNote &b) {
-  const uint8_t *n1 = sm.note_buf + a.off + 12, *n2 = sm.note_buf + b.off + 12;
-  int l = (int)(a.namesz < b.namesz ? a.namesz : b.namesz) - 3;
-  for (int i = 0; i < l; i++)
-    if (n1[3 + i] != n2[3 + i]) return (int)n1[3 + i] - (int)n2[3 + i];
+  const int c = cmp_note_names(sm, a, b);
+  if (c) return c;
   if (a.end < b.start) return -1;
   if (a.start > b.end) return 1;
   if (a.start < b.start) return -1;
@@ -190,38 +202,46 @@ __device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
   if (a.start > b.start) return 1;
   if (a.end > b.end) return -1;                        // larger ranges first
   if (a.end < b.end) return 1;
-  bool v1 = note_is_version(sm, a), v2 = note_is_version(sm, b);
-  if (v1 && !v2) return -1;
-  if (!v1 && v2) return 1;
+  if (a.ver && !b.ver) return -1;
+  if (!a.ver && b.ver) return 1;
   return 0;
 }
 
 // objcopy sorts the notes with libc qsort(); its first comparator is not antisymmetric for nested
 // ranges, so the result depends on the exact comparison sequence.  This image's glibc 2.39 qsort
 // is the classic top-down merge sort (msort.c: n1 = n / 2, sort both halves, merge taking the left
-// element while cmp(left, right) <= 0).  Restated here on the note permutation, run by one lane
-// (n <= 320: a few thousand comparisons).  `second` selects the comparator.
-__device__ void msort_notes(PlanSmem &sm, int n, bool second) {
-  struct Frame { uint16_t lo, n; uint8_t stage; };
-  Frame stack[12];
-  int sp = 0;
-  stack[sp++] = Frame{0, (uint16_t)n, 0};
-  while (sp > 0) {
-    Frame &f = stack[sp - 1];
-    if (f.n <= 1) { sp--; continue; }
-    const int n1 = f.n / 2, n2 = f.n - n1;
-    if (f.stage == 0) { f.stage = 1; stack[sp++] = Frame{f.lo, (uint16_t)n1, 0}; continue; }
-    if (f.stage == 1) { f.stage = 2; stack[sp++] = Frame{(uint16_t)(f.lo + n1), (uint16_t)n2, 0}; continue; }
-    int i = f.lo, j = f.lo + n1, k = 0, r1 = n1, r2 = n2;
-    while (r1 > 0 && r2 > 0) {
-      const DNote &a = sm.notes[sm.note_perm[i]], &b = sm.notes[sm.note_perm[j]];
-      const int c = second ? cmp_by_addr(sm, a, b) : cmp_by_attr(sm, a, b);
-      if (c <= 0) { sm.note_tmp[k++] = sm.note_perm[i++]; r1--; }
-      else { sm.note_tmp[k++] = sm.note_perm[j++]; r2--; }
+// element while cmp(left, right) <= 0).  The recursion tree is restated level by level: at depth d the
+// segment of node k is found by halving [0, n) along the bits of k, all merges of one depth are
+// independent and run on different lanes, deepest level first -- the same comparisons in the same
+// order inside every merge as the recursive routine, 2n instead of n log n merge steps deep.
+__device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int *hi) {
+  int l = 0, h = n;
+  for (int b = depth - 1; b >= 0; b--) {
+    const int mid = l + (h - l) / 2;
+    if ((k >> b) & 1) l = mid; else h = mid;
+  }
+  *lo = l; *hi = h;
+}
+__device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
+  int depth = 0;
+  while ((1 << depth) < n) depth++;
+  for (int d = depth - 1; d >= 0; d--) {
+    for (int k = lane; k < (1 << d); k += 32) {
+      int lo, hi;
+      msort_node(n, d, k, &lo, &hi);
+      const int n1 = (hi - lo) / 2;
+      int i = lo, j = lo + n1, w = lo, r1 = n1, r2 = (hi - lo) - n1;
+      if (r1 == 0 || r2 == 0) continue;
+      while (r1 > 0 && r2 > 0) {
+        const DNote &a = sm.notes[sm.note_perm[i]], &b = sm.notes[sm.note_perm[j]];
+        const int c = second ? cmp_by_addr(sm, a, b) : cmp_by_attr(sm, a, b);
+        if (c <= 0) { sm.note_tmp[w++] = sm.note_perm[i++]; r1--; }
+        else { sm.note_tmp[w++] = sm.note_perm[j++]; r2--; }
+      }
+      while (r1 > 0) { sm.note_tmp[w++] = sm.note_perm[i++]; r1--; }
+      for (int q = lo; q < w; q++) sm.note_perm[q] = sm.note_tmp[q];  // the tail of the right run is already in place
     }
-    while (r1 > 0) { sm.note_tmp[k++] = sm.note_perm[i++]; r1--; }
-    for (int q = 0; q < k; q++) sm.note_perm[f.lo + q] = sm.note_tmp[q];
-    sp--;
+    __syncwarp();
   }
 }
 
@@ -244,7 +264,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
       if (type != 0x100 && type != 0x101) { s_err = 1; break; }
       if ((uint64_t)padded + descsz + 12 > remain) { s_err = 1; break; }
-      if (namesz < 2) { s_err = 1; break; }
+      if (namesz < 3) { s_err = 1; break; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
       const uint8_t *nm = h + 12, *desc = h + 12 + padded;
       remain -= 12 + padded + descsz;
       p += 12 + padded + descsz;
@@ -295,8 +315,28 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     return size;
   }
   const int n = s_n;
+  // per-note comparison aids, one note per lane-iteration
+  for (int i = lane; i < n; i += 32) {
+    DNote &d = sm.notes[i];
+    const uint8_t *nm = sm.note_buf + d.off + 12;
+    uint64_t key = 0;
+    for (int q = 0; q < 8; q++) key = (key << 8) | (3 + q < (int)d.namesz ? nm[3 + q] : 0);
+    d.key = key;
+    d.ver = (d.namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) ? 1 : 0;
+    int cls = i;
+    for (int j = 0; j < i; j++) {
+      const DNote &o = sm.notes[j];
+      if (o.namesz != d.namesz) continue;
+      const uint8_t *om = sm.note_buf + o.off + 12;
+      bool same = true;
+      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
+      if (same) { cls = j; break; }
+    }
+    d.cls = (uint16_t)cls;
+  }
+  __syncwarp();
+  warp_msort_notes(sm, n, false, lane);
   if (lane == 0) {
-    msort_notes(sm, n, false);
     for (int i = 0; i < n; i++) {
       DNote &pn = sm.notes[sm.note_perm[i]];
       if (pn.type == 0) continue;
@@ -305,11 +345,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       for (int b = i - 1; b >= 0; b--) {
         DNote &back = sm.notes[sm.note_perm[b]];
         if (back.type == 0) continue;
-        if (back.namesz != pn.namesz) break;
-        const uint8_t *n1 = sm.note_buf + back.off + 12, *n2 = sm.note_buf + pn.off + 12;
-        bool same = true;
-        for (int q = 0; q < pn.namesz; q++) if (n1[q] != n2[q]) { same = false; break; }
-        if (!same) break;
+        if (back.cls != pn.cls) break;  // a different attribute name ends the search
         if (back.start == pn.start && back.end == pn.end) { pn.type = 0; break; }
         if (pn.start >= back.start && pn.end <= back.end) { pn.type = 0; break; }
         bool merge;
@@ -326,37 +362,44 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       }
     }
   }
+  __syncwarp();
+  warp_msort_notes(sm, n, true, lane);
   if (lane == 0) {
-    msort_notes(sm, n, true);
+    // output offsets and range elision (depends on the previous surviving note): serial and cheap
     uint32_t w = 0;
     uint64_t ps = 0, pe = 0;
     for (int i = 0; i < n; i++) {
       const DNote &pn = sm.notes[sm.note_perm[i]];
-      if (pn.type == 0) continue;
-      bool elide = (pn.start == ps && pn.end == pe);
-      uint32_t padded = (pn.namesz + 3u) & ~3u;
-      wr32(out + w, pn.namesz);
-      wr32(out + w + 4, elide ? 0u : 16u);
-      wr32(out + w + 8, pn.type);
-      w += 12;
-      const uint8_t *nm = sm.note_buf + pn.off + 12;
-      for (uint32_t q = 0; q < padded; q++) out[w + q] = q < pn.namesz ? nm[q] : 0;
-      w += padded;
-      if (!elide) {
-        wr64(out + w, pn.start);
-        wr64(out + w + 8, pn.end);
-        w += 16;
-        ps = pn.start;
-        pe = pn.end;
-      }
+      if (pn.type == 0) { sm.note_tmp[i] = 0xffff; continue; }
+      const bool elide = (pn.start == ps && pn.end == pe);
+      sm.note_tmp[i] = (uint16_t)((w >> 2) | (elide ? 0x8000u : 0u));  // offsets are multiples of 4, < 64 KB
+      w += 12 + ((pn.namesz + 3u) & ~3u) + (elide ? 0u : 16u);
+      if (!elide) { ps = pn.start; pe = pn.end; }
     }
     s_newsize = w;
   }
   __syncwarp();
-  if (s_newsize < size) return s_newsize;
-  for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+  if (s_newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
+    for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+    __syncwarp();
+    return size;
+  }
+  for (int i = lane; i < n; i += 32) {
+    const uint16_t t = sm.note_tmp[i];
+    if (t == 0xffff) continue;
+    const DNote &pn = sm.notes[sm.note_perm[i]];
+    const bool elide = (t & 0x8000u) != 0;
+    uint8_t *o = out + ((uint32_t)(t & 0x7fffu) << 2);
+    const uint32_t padded = (pn.namesz + 3u) & ~3u;
+    wr32(o, pn.namesz);
+    wr32(o + 4, elide ? 0u : 16u);
+    wr32(o + 8, pn.type);
+    const uint8_t *nm = sm.note_buf + pn.off + 12;
+    for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? nm[q] : 0;
+    if (!elide) { wr64(o + 12 + padded, pn.start); wr64(o + 20 + padded, pn.end); }
+  }
   __syncwarp();
-  return size;
+  return s_newsize;
 }
 
 #define LB2_FAIL(code) do { sm.fail = (code); } while (0)

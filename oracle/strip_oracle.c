@@ -228,7 +228,7 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
     if (((pn->descsz + 3) & ~3u) != pn->descsz) goto bad;
     if (pn->type != NT_OPEN && pn->type != NT_FUNC) goto bad;
     if ((uint64_t)pn->padded_namesz + pn->descsz + 12 > remain) goto bad;
-    if (pn->namesz < 2) goto bad;
+    if (pn->namesz < 3) goto bad; /* objcopy accepts 2 and then memcmp()s namesz - 3 bytes: out of contract */
     pn->name = p + 12;
     const uint8_t *desc = p + 12 + pn->padded_namesz;
     remain -= 12 + (uint64_t)pn->padded_namesz + pn->descsz;

@@ -114,6 +114,13 @@ def build_variants(outdir):
                            "--add-section", ".stabfoo=" + blob, "--add-section", ".comment2=" + blob, base, ex],
                           capture_output=True).returncode == 0:
             out["c_extra_sections"] = ex
+        # more sections than the device planner holds in shared memory (64): planner-limit class
+        many = os.path.join(outdir, "c_many_sections.so")
+        args = []
+        for i in range(70):
+            args += ["--add-section", ".lb2.extra%02d=%s" % (i, blob)]
+        if subprocess.run(["objcopy"] + args + [base, many], capture_output=True).returncode == 0:
+            out["c_many_sections"] = many
     return out
 
 
