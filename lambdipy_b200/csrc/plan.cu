@@ -9,6 +9,9 @@
 // This is product code: it shares nothing with oracle/ (an independent CPU restatement used only
 // by the tests to check this kernel).
 #include "lb2_common.cuh"
+#ifdef LB2_PLAN_TIMING
+#include <cstdio>
+#endif
 
 namespace lb2 {
 
@@ -223,6 +226,9 @@ __device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int
   *lo = l; *hi = h;
 }
 __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
+  const DNote *__restrict__ notes = sm.notes;   // hoisted: PlanSmem only holds pointers to the note workspace
+  uint16_t *__restrict__ perm = sm.note_perm;
+  uint16_t *__restrict__ tmp = sm.note_tmp;
   int depth = 0;
   while ((1 << depth) < n) depth++;
   for (int d = depth - 1; d >= 0; d--) {
@@ -232,14 +238,23 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
       const int n1 = (hi - lo) / 2;
       int i = lo, j = lo + n1, w = lo, r1 = n1, r2 = (hi - lo) - n1;
       if (r1 == 0 || r2 == 0) continue;
-      while (r1 > 0 && r2 > 0) {
-        const DNote &a = sm.notes[sm.note_perm[i]], &b = sm.notes[sm.note_perm[j]];
+      // the heads of both runs live in registers; only the side that advanced is reloaded
+      uint16_t pa = perm[i], pb = perm[j];
+      DNote a = notes[pa], b = notes[pb];
+      while (true) {
         const int c = second ? cmp_by_addr(sm, a, b) : cmp_by_attr(sm, a, b);
-        if (c <= 0) { sm.note_tmp[w++] = sm.note_perm[i++]; r1--; }
-        else { sm.note_tmp[w++] = sm.note_perm[j++]; r2--; }
+        if (c <= 0) {
+          tmp[w++] = pa; i++;
+          if (--r1 == 0) break;
+          pa = perm[i]; a = notes[pa];
+        } else {
+          tmp[w++] = pb; j++;
+          if (--r2 == 0) break;
+          pb = perm[j]; b = notes[pb];
+        }
       }
-      while (r1 > 0) { sm.note_tmp[w++] = sm.note_perm[i++]; r1--; }
-      for (int q = lo; q < w; q++) sm.note_perm[q] = sm.note_tmp[q];  // the tail of the right run is already in place
+      while (r1 > 0) { tmp[w++] = perm[i++]; r1--; }
+      for (int q = lo; q < w; q++) perm[q] = tmp[q];  // the tail of the right run is already in place
     }
     __syncwarp();
   }
@@ -247,9 +262,23 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
 
 // Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
 // Returns the new size; *err != 0 when objcopy would report corrupt notes.  Warp-collective.
+#ifdef LB2_PLAN_TIMING
+#define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
+#else
+#define LB2_NT(k) do { } while (0)
+#endif
 __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out, int *err, int lane) {
   __shared__ int s_n, s_err, s_skip;
   __shared__ uint32_t s_newsize;
+  DNote *__restrict__ notes = sm.notes;          // hoisted out of shared memory once
+  uint16_t *__restrict__ perm = sm.note_perm;
+  uint16_t *__restrict__ tmp = sm.note_tmp;
+  const uint8_t *__restrict__ nbuf = sm.note_buf;
+  const int note_cap = sm.note_cap_n;
+#ifdef LB2_PLAN_TIMING
+  long long nt_[8];
+#endif
+  LB2_NT(0);
   if (lane == 0) {
     s_err = 0; s_skip = 0; s_n = 0;
     int n = 0;
@@ -257,9 +286,10 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     unsigned v1 = 0, v2 = 0, v3 = 0;
     uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
     while (remain >= 12) {
-      if (n >= sm.note_cap_n) { s_err = 2; break; }
-      const uint8_t *h = sm.note_buf + p;
-      uint32_t namesz = rd32(h), descsz = rd32(h + 4), type = rd32(h + 8);
+      if (n >= note_cap) { s_err = 2; break; }
+      const uint8_t *h = nbuf + p;  // p stays a multiple of 4: aligned word loads
+      const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);
+      uint32_t namesz = hw[0], descsz = hw[1], type = hw[2];
       uint32_t padded = (namesz + 3) & ~3u;
       if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
       if (type != 0x100 && type != 0x101) { s_err = 1; break; }
@@ -268,8 +298,8 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       const uint8_t *nm = h + 12, *desc = h + 12 + padded;
       remain -= 12 + padded + descsz;
       p += 12 + padded + descsz;
-      DNote &d = sm.notes[n];
-      d.off = (uint16_t)(h - sm.note_buf);
+      DNote &d = notes[n];
+      d.off = (uint16_t)(h - nbuf);
       d.namesz = (uint16_t)namesz;
       d.type = type;
       if (namesz > 2 && nm[0] == '$' && nm[1] == 1 && nm[2] == '1') v1++;
@@ -279,10 +309,11 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
         else { s_err = 1; break; }
       }
       uint64_t start, end;
+      const uint32_t *dw = reinterpret_cast<const uint32_t *>(desc);
       if (descsz == 0) start = end = 0;
-      else if (descsz == 4) { start = rd32(desc); end = ~0ull; }
-      else if (descsz == 8) { start = rd32(desc); end = rd32(desc + 4); }
-      else if (descsz == 16) { start = rd64(desc); end = rd64(desc + 8); }
+      else if (descsz == 4) { start = dw[0]; end = ~0ull; }
+      else if (descsz == 8) { start = dw[0]; end = dw[1]; }
+      else if (descsz == 16) { start = (uint64_t)dw[0] | ((uint64_t)dw[1] << 32); end = (uint64_t)dw[2] | ((uint64_t)dw[3] << 32); }
       else { s_err = 1; break; }
       if (start > end) start = end;
       if (type == 0x100) {
@@ -297,7 +328,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
         d.end = pfe;
       }
       if (nm[namesz - 1] != 0) { s_err = 1; break; }
-      sm.note_perm[n] = (uint16_t)n;
+      perm[n] = (uint16_t)n;
       n++;
     }
     if (!s_err && remain != 0) s_err = 1;
@@ -311,23 +342,36 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   __syncwarp();
   if (s_err) { *err = s_err; return size; }
   if (s_skip || size < 12) {
-    for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
     return size;
   }
   const int n = s_n;
+  LB2_NT(1);
   // per-note comparison aids, one note per lane-iteration
   for (int i = lane; i < n; i += 32) {
-    DNote &d = sm.notes[i];
-    const uint8_t *nm = sm.note_buf + d.off + 12;
+    DNote &d = notes[i];
+    const uint8_t *nm = nbuf + d.off + 12;
     uint64_t key = 0;
-    for (int q = 0; q < 8; q++) key = (key << 8) | (3 + q < (int)d.namesz ? nm[3 + q] : 0);
+    uint32_t hsh = 2166136261u;
+    for (int q = 0; q < (int)d.namesz; q++) {
+      hsh = (hsh ^ nm[q]) * 16777619u;
+      if (q >= 3 && q < 11) key = (key << 8) | nm[q];
+    }
+    if (d.namesz <= 3) key = 0; else if (d.namesz < 11) key <<= 8 * (11 - d.namesz);
     d.key = key;
     d.ver = (d.namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) ? 1 : 0;
+    d.pad = (uint8_t)hsh;             // low hash byte, cheap first filter
+    tmp[i] = (uint16_t)(hsh >> 8);
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    DNote &d = notes[i];
+    const uint8_t *nm = nbuf + d.off + 12;
     int cls = i;
     for (int j = 0; j < i; j++) {
-      const DNote &o = sm.notes[j];
-      if (o.namesz != d.namesz) continue;
-      const uint8_t *om = sm.note_buf + o.off + 12;
+      const DNote &o = notes[j];
+      if (o.namesz != d.namesz || o.pad != d.pad || tmp[j] != tmp[i]) continue;
+      const uint8_t *om = nbuf + o.off + 12;
       bool same = true;
       for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
       if (same) { cls = j; break; }
@@ -335,15 +379,17 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     d.cls = (uint16_t)cls;
   }
   __syncwarp();
+  LB2_NT(2);
   warp_msort_notes(sm, n, false, lane);
+  LB2_NT(3);
   if (lane == 0) {
     for (int i = 0; i < n; i++) {
-      DNote &pn = sm.notes[sm.note_perm[i]];
+      DNote &pn = notes[perm[i]];
       if (pn.type == 0) continue;
       if (pn.start == pn.end) { pn.type = 0; continue; }
       int iter = 0;
       for (int b = i - 1; b >= 0; b--) {
-        DNote &back = sm.notes[sm.note_perm[b]];
+        DNote &back = notes[perm[b]];
         if (back.type == 0) continue;
         if (back.cls != pn.cls) break;  // a different attribute name ends the search
         if (back.start == pn.start && back.end == pn.end) { pn.type = 0; break; }
@@ -363,16 +409,18 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     }
   }
   __syncwarp();
+  LB2_NT(4);
   warp_msort_notes(sm, n, true, lane);
+  LB2_NT(5);
   if (lane == 0) {
     // output offsets and range elision (depends on the previous surviving note): serial and cheap
     uint32_t w = 0;
     uint64_t ps = 0, pe = 0;
     for (int i = 0; i < n; i++) {
-      const DNote &pn = sm.notes[sm.note_perm[i]];
-      if (pn.type == 0) { sm.note_tmp[i] = 0xffff; continue; }
+      const DNote &pn = notes[perm[i]];
+      if (pn.type == 0) { tmp[i] = 0xffff; continue; }
       const bool elide = (pn.start == ps && pn.end == pe);
-      sm.note_tmp[i] = (uint16_t)((w >> 2) | (elide ? 0x8000u : 0u));  // offsets are multiples of 4, < 64 KB
+      tmp[i] = (uint16_t)((w >> 2) | (elide ? 0x8000u : 0u));  // offsets are multiples of 4, < 64 KB
       w += 12 + ((pn.namesz + 3u) & ~3u) + (elide ? 0u : 16u);
       if (!elide) { ps = pn.start; pe = pn.end; }
     }
@@ -380,29 +428,38 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   }
   __syncwarp();
   if (s_newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
-    for (uint32_t i = lane; i < size; i += 32) out[i] = sm.note_buf[i];
+    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
     __syncwarp();
     return size;
   }
   for (int i = lane; i < n; i += 32) {
-    const uint16_t t = sm.note_tmp[i];
+    const uint16_t t = tmp[i];
     if (t == 0xffff) continue;
-    const DNote &pn = sm.notes[sm.note_perm[i]];
+    const DNote &pn = notes[perm[i]];
     const bool elide = (t & 0x8000u) != 0;
     uint8_t *o = out + ((uint32_t)(t & 0x7fffu) << 2);
     const uint32_t padded = (pn.namesz + 3u) & ~3u;
     wr32(o, pn.namesz);
     wr32(o + 4, elide ? 0u : 16u);
     wr32(o + 8, pn.type);
-    const uint8_t *nm = sm.note_buf + pn.off + 12;
+    const uint8_t *nm = nbuf + pn.off + 12;
     for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? nm[q] : 0;
     if (!elide) { wr64(o + 12 + padded, pn.start); wr64(o + 20 + padded, pn.end); }
   }
   __syncwarp();
+  LB2_NT(6);
+#ifdef LB2_PLAN_TIMING
+  if (lane == 0 && blockIdx.x == 0) printf("  notes n=%d: parse=%lld aids=%lld sort1=%lld merge=%lld sort2=%lld out=%lld\n", n, nt_[1]-nt_[0], nt_[2]-nt_[1], nt_[3]-nt_[2], nt_[4]-nt_[3], nt_[5]-nt_[4], nt_[6]-nt_[5]);
+#endif
   return s_newsize;
 }
 
 #define LB2_FAIL(code) do { sm.fail = (code); } while (0)
+#ifdef LB2_PLAN_TIMING
+#define LB2_T(k) do { __syncwarp(); if (lane == 0) t_[k] = clock64(); } while (0)
+#else
+#define LB2_T(k) do { } while (0)
+#endif
 
 template <int NB, int NN, bool RETRY_PASS>
 __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
@@ -412,6 +469,11 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   const uint32_t f = blockIdx.x;
   if (f >= a.n_files) return;
   if (RETRY_PASS && a.status[f] != ST_RETRY_BIG_NOTES) return;
+#ifdef LB2_PLAN_TIMING
+  long long t_[16];
+  for (int q = 0; q < 16; q++) t_[q] = 0;
+#endif
+  LB2_T(0);
   if (lane == 0) {
     sm.notes = ns.notes; sm.note_perm = ns.perm; sm.note_tmp = ns.tmp; sm.note_buf = ns.buf;
     sm.note_cap_bytes = NB; sm.note_cap_n = NN;
@@ -424,6 +486,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   if (lane == 0) { sm.fail = 0; sm.note_tie = 0; }
   __syncwarp();
 
+  LB2_T(1);
   // ---- A. Ehdr
   if (n < 64) { if (lane == 0) { a.status[f] = ST_NOT_ELF; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
   if (lane < 4) reinterpret_cast<uint4 *>(&sm.eh)[lane] = __ldg(reinterpret_cast<const uint4 *>(in) + lane);
@@ -445,6 +508,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   if (st != ST_OK) { if (lane == 0) { a.status[f] = st; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
   const int shnum = eh.e_shnum, phnum = eh.e_phnum;
 
+  LB2_T(2);
   // ---- B. section headers, program headers, section names: coalesced vector loads into smem
   warp_g2s(sm.sh, in + eh.e_shoff, (uint32_t)shnum * 64, lane);
   if (phnum) warp_g2s(sm.ph, in + eh.e_phoff, (uint32_t)phnum * 56, lane);
@@ -464,6 +528,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
   const uint32_t strsz = sm.strsz;
 
+  LB2_T(3);
   // ---- C. R1 keep/drop mask, lane i <-> sections i and i+32; verdicts combined by ballot
   {
     int err_mal = 0, err_uns = 0;
@@ -496,6 +561,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
   __syncwarp();
 
+  LB2_T(4);
   // ---- D. R2 output order (hoist of a later dynsym in front of the first section linking to
   //         it ... BFD: in front of the first REL/RELA that uses it) and new section indices.
   if (lane == 0) {
@@ -519,6 +585,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __syncwarp();
   const int nk = sm.nk;
 
+  LB2_T(5);
   // ---- E. R9 build-attribute note merging (sizes feed the layout)
   if (!(a.flags & 1u)) {
     uint32_t scr_used = 0;
@@ -530,8 +597,14 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
         if (lane == 0) LB2_FAIL((!RETRY_PASS && h.sh_size <= MAX_NOTE_BYTES && scr_used + h.sh_size <= MAX_NOTE_BYTES) ? ST_RETRY_BIG_NOTES : ST_PLANNER_LIMIT);
         break;
       }
+#ifdef LB2_PLAN_TIMING
+      long long g0 = clock64();
+#endif
       warp_g2s(sm.note_buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
       __syncwarp();
+#ifdef LB2_PLAN_TIMING
+      if (lane == 0 && f == 0) printf("  notes g2s %u bytes: %lld cycles\n", (unsigned)h.sh_size, clock64() - g0);
+#endif
       int err = 0;
       uint8_t *dst = scr + SCR_NOTES + scr_used;
       uint32_t ns = merge_build_notes(sm, (uint32_t)h.sh_size, dst, &err, lane);
@@ -551,6 +624,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     return;
   }
 
+  LB2_T(6);
   // ---- F. which PT_LOAD carries each kept alloc section (lane-parallel), which phdrs survive (R11)
   {
     int err = 0;
@@ -584,6 +658,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __syncwarp();
   const int new_phnum = sm.new_phnum;
 
+  LB2_T(7);
   // ---- G. R10: PT_LOAD layout (sequential in the file cursor)
   if (lane == 0) {
     uint64_t cur = 64 + (uint64_t)new_phnum * 56, last_vaddr = 0;
@@ -636,6 +711,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __syncwarp();
   if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
 
+  LB2_T(8);
   // ---- H. R12: every other program header, one per lane
   if (lane < phnum && sm.pkeep[lane] && sm.ph[lane].p_type != PT_LOAD) {
     const int j = lane;
@@ -703,6 +779,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
   __syncwarp();
 
+  LB2_T(9);
   // ---- I. R4 non-alloc sections packed behind the last allocated byte (align-then-add chain)
   if (lane == 0) {
     uint64_t cur = sm.cur;
@@ -718,6 +795,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
   __syncwarp();
 
+  LB2_T(10);
   // ---- J. R6 .shstrtab: unique names (entry 0 = ".shstrtab"), reversed-string rank sort across
   //         lanes, suffix merge, offsets in insertion order.
   for (int k = 1 + lane; k < nk; k += 32) {
@@ -795,6 +873,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       for (int q = 0; q < sm.ent_len[e]; q++) scr[SCR_STR + sm.ent_off[e] + q] = (uint8_t)s[q];
     }
 
+  LB2_T(11);
   // ---- K. R7 new section-header table (one header per lane-iteration), R8 Ehdr, new Phdr table
   for (int k = lane; k <= nk; k += 32) {
     Shdr h;
@@ -866,6 +945,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       }
   }
 
+  LB2_T(12);
   // ---- L. extents: every output byte is produced exactly once -- copied from the input arena,
   //         copied from the scratch slot, or zero-filled (BFD leaves gaps as file holes).
   if (lane == 0) {
@@ -898,6 +978,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __syncwarp();
   if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
 
+  LB2_T(13);
   // ---- M. tiles: warp-shuffle prefix sum over the per-extent tile counts gives every extent its
   //         slot range in the global tile list; one atomicAdd per file reserves the range.
   const int n_ext = sm.n_ext;
@@ -940,6 +1021,14 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       out[k] = t;
     }
   }
+  LB2_T(14);
+#ifdef LB2_PLAN_TIMING
+  if (lane == 0 && f == 0) {
+    printf("plan timing (cycles) retry=%d:", (int)RETRY_PASS);
+    for (int q = 1; q <= 14; q++) printf(" %c=%lld", q <= 13 ? 'A' + q - 1 : 'Z', t_[q] - t_[q - 1]);
+    printf(" total=%lld\n", t_[14] - t_[0]);
+  }
+#endif
   if (lane == 0) {
     a.out_size[f] = sm.total;
     a.status[f] = ST_OK;
