@@ -49,51 +49,91 @@ def peaks():
 
 # ---------------------------------------------------------------- clocks during the timed region
 class ClockSampler:
+    """SM clocks and throttle reasons DURING the timed regions.  NVML from a thread (a few microseconds
+    per sample); `nvidia-smi -lms` as fallback -- polling nvidia-smi at 100 ms measurably slowed the
+    sampled GPU's kernels in the 8-GPU runs, NVML queries do not."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="lb2_clocks_", suffix=".csv")
-        self.proc = None
         self.idx = gpu_index
+        self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                r = get_reasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
         try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.path = tempfile.mktemp(prefix="lb2_clocks_", suffix=".csv")
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.proc:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        try:
-            with open(self.path) as f:
-                for line in f:
-                    p = [x.strip() for x in line.split(",")]
-                    if len(p) < 9:
-                        continue
-                    try:
-                        sm.append(float(p[1])); mx.append(float(p[2]))
-                    except ValueError:
-                        continue
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            out["source"] = "nvml"
+        elif self.proc:
+            out["source"] = "nvidia-smi"
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.close()
+            try:
+                with open(self.path) as f:
+                    for line in f:
+                        p = [x.strip() for x in line.split(",")]
+                        if len(p) < 9:
+                            continue
+                        try:
+                            self.sm.append(float(p[1])); self.mx.append(float(p[2]))
+                        except ValueError:
+                            continue
+                        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                            if v.lower().startswith("active"):
+                                self.reasons.add(name)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        if self.sm:
+            out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=max(self.mx), reasons=sorted(self.reasons), samples=len(self.sm))
         return out
 
 
@@ -195,7 +235,7 @@ def workload_config(a, world):
 
 
 def run_b200(a, rank, local_rank, world):
-    os.environ["NCCL_DEBUG"] = os.environ.get("LB2_NCCL_DEBUG", "WARN")  # keep NCCL banners off stdout (one JSON line)
+    os.environ["NCCL_DEBUG"] = os.environ.get("LB2_NCCL_DEBUG", "NONE")  # NCCL prints its version banner on stdout at any level >= VERSION; bench prints ONE JSON line
     import numpy as np
     import torch
     from lambdipy_b200 import _native as N
@@ -214,6 +254,12 @@ def run_b200(a, rank, local_rank, world):
     sptr = C.c_void_p(stream.cuda_stream)
     counts = torch.zeros(4, dtype=torch.int64, device="cuda")
     gathered = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+    # The allgather of the per-rank counters runs on a side stream: the next batch does not have to
+    # wait for the slowest rank's counters (files never move between GPUs); the timed region ends
+    # only after every step's allgather has completed.
+    side = torch.cuda.Stream() if world > 1 else None
+    ring = [(torch.zeros(4, dtype=torch.int64, device="cuda"), torch.zeros(4 * world, dtype=torch.int64, device="cuda")) for _ in range(8)] if world > 1 else []
+    ring_pos = [0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,8 +271,11 @@ def run_b200(a, rank, local_rank, world):
         batch.strip_async(stream=sptr)
         st = batch.results()
         if dist:  # the one collective of the path: per-rank byte counts (32 bytes per rank)
-            counts.copy_(torch.tensor([st["in_bytes"], st["out_bytes"], st["n_ok"], st["n_unsupported"]], dtype=torch.int64), non_blocking=True)
-            dist.all_gather_into_tensor(gathered, counts)
+            c, g = ring[ring_pos[0] % len(ring)]
+            ring_pos[0] += 1
+            with torch.cuda.stream(side):
+                c.copy_(torch.tensor([st["in_bytes"], st["out_bytes"], st["n_ok"], st["n_unsupported"]], dtype=torch.int64), non_blocking=True)
+                dist.all_gather_into_tensor(g, c)
         return st
 
     for _ in range(max(a.warmup, 3)):
@@ -243,14 +292,27 @@ def run_b200(a, rank, local_rank, world):
     for _ in range(a.steps):
         st = step()
         compact_ms.append(st["compact_ms"]); plan_ms.append(st["plan_ms"])
+    if side is not None:
+        stream.wait_stream(side)  # every step's allgather is inside the timed region
     e1.record(stream)
     barrier()
+    if dist:
+        g = ring[(ring_pos[0] - 1) % len(ring)][1].cpu().numpy().reshape(world, 4)
+        assert int(g[:, 2].sum()) == a.files_per_gpu * world and int(g[:, 3].sum()) == 0, g
     dev_ms = e0.elapsed_time(e1)
     if a.profile_mode:
+        from lambdipy_b200.sharding import gather_counts
+        per_rank = gather_counts([int(1e3 * sum(compact_ms) / len(compact_ms)), int(1e3 * sum(plan_ms) / len(plan_ms)),
+                                  st["copy_bytes"] + st["out_bytes"], int(1e3 * dev_ms / a.steps)], device="cuda")
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": dev_ms / a.steps, "compact_ms": compact_ms, "plan_ms": plan_ms,
+                              "per_rank_[compact_us, plan_us, alg_bytes, step_us]": per_rank.tolist(),
+                              "per_rank_compact_frac": [float(r[2]) / 1e9 / (r[0] / 1e6) / peaks()[0] for r in per_rank.tolist()],
                               "note": "not a bench value"}))
         batch.close()
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
         return 0
 
     # ---- end to end through host buffers
