@@ -497,12 +497,16 @@ static void dedupe(std::vector<TreeFile> &files) {
   files.resize(w);
 }
 
-static bool read_file(const std::string &p, uint8_t *dst, uint64_t n) {
+// Files are read and written in <= 8 MB pieces so that one 900 MB library is handled by many I/O
+// threads instead of one (the tree of BASELINE config 3 is dominated by two such files).
+static const uint64_t IO_PIECE = 8ull << 20;
+
+static bool read_piece(const std::string &p, uint8_t *dst, uint64_t off, uint64_t n) {
   int fd = open(p.c_str(), O_RDONLY | O_CLOEXEC);
   if (fd < 0) return false;
   uint64_t got = 0;
   while (got < n) {
-    ssize_t r = read(fd, dst + got, n - got);
+    ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
     if (r <= 0) { if (r < 0 && errno == EINTR) continue; break; }
     got += (uint64_t)r;
   }
@@ -510,8 +514,22 @@ static bool read_file(const std::string &p, uint8_t *dst, uint64_t n) {
   return got == n;
 }
 
+static bool write_piece(const char *tmp, const uint8_t *src, uint64_t off, uint64_t n) {
+  int fd = open(tmp, O_WRONLY | O_CLOEXEC);
+  if (fd < 0) return false;
+  uint64_t put = 0;
+  bool ok = true;
+  while (put < n) {
+    ssize_t r = pwrite(fd, src + put, n - put, (off_t)(off + put));
+    if (r <= 0) { if (r < 0 && errno == EINTR) continue; ok = false; break; }
+    put += (uint64_t)r;
+  }
+  close(fd);
+  return ok;
+}
+
 // temp file in the same directory + rename, mode preserved (what strip does; mtime is not kept)
-static bool replace_file(const std::string &p, const uint8_t *src, uint64_t n, mode_t mode) {
+[[maybe_unused]] static bool replace_file(const std::string &p, const uint8_t *src, uint64_t n, mode_t mode) {
   std::string tmp = p + ".lb2XXXXXX";
   std::vector<char> t(tmp.begin(), tmp.end());
   t.push_back(0);
@@ -585,8 +603,16 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
   }
   const int io_threads = (int)env_u64("LB2_IO_THREADS", std::max(4u, std::min(32u, std::thread::hardware_concurrency())));
   std::atomic<int> read_fail{0};
-  parallel_for(n, io_threads, [&](size_t i) {
-    if (!read_file(files[i].path, ctx->h_tree_in + off[i], sizes[i])) read_fail++;
+  struct Piece { uint32_t file; uint64_t off, len; };
+  std::vector<Piece> rpieces;
+  for (uint32_t i = 0; i < n; i++)
+    for (uint64_t o = 0; o < sizes[i] || (o == 0 && sizes[i] == 0); o += IO_PIECE) {
+      rpieces.push_back({i, o, std::min(IO_PIECE, sizes[i] - o)});
+      if (sizes[i] == 0) break;
+    }
+  parallel_for(rpieces.size(), io_threads, [&](size_t k) {
+    const Piece &pc = rpieces[k];
+    if (pc.len && !read_piece(files[pc.file].path, ctx->h_tree_in + off[pc.file] + pc.off, pc.off, pc.len)) read_fail++;
   });
   if (read_fail) { ctx->err = "could not read some selected files"; return LB2_E_IO; }
   st.walk_read_s = now_s() - t0;
@@ -635,11 +661,38 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
   std::vector<uint32_t> fallback;
   for (uint32_t i = 0; i < n; i++) if (status[i] != LB2_ST_OK) fallback.push_back(i);
   if (!(flags & LB2_TREE_DRY_RUN)) {
-    parallel_for(n, io_threads, [&](size_t i) {
-      if (status[i] != LB2_ST_OK) return;
-      if (replace_file(files[i].path, ctx->h_tree_out + out_off[i], out_sizes[i], files[i].mode)) {
-        n_gpu++; in_b += sizes[i]; out_b += out_sizes[i];
-      } else n_failed++;
+    // temp file next to the target (pre-sized), pieces written in parallel, then fchmod + rename by
+    // whichever thread finishes the file's last piece -- what strip does, minus the single thread
+    std::vector<std::string> tmp_path(n);
+    std::vector<std::atomic<int>> remaining(n);
+    std::vector<std::atomic<int>> piece_fail(n);
+    std::vector<Piece> wpieces;
+    for (uint32_t i = 0; i < n; i++) {
+      remaining[i] = 0; piece_fail[i] = 0;
+      if (status[i] != LB2_ST_OK) continue;
+      std::string t = files[i].path + ".lb2XXXXXX";
+      std::vector<char> tb(t.begin(), t.end());
+      tb.push_back(0);
+      int fd = mkstemp(tb.data());
+      if (fd < 0) { n_failed++; continue; }
+      if (ftruncate(fd, (off_t)out_sizes[i]) != 0) { close(fd); unlink(tb.data()); n_failed++; continue; }
+      close(fd);
+      tmp_path[i] = tb.data();
+      int cnt = 0;
+      for (uint64_t o = 0; o < out_sizes[i]; o += IO_PIECE) { wpieces.push_back({i, o, std::min(IO_PIECE, out_sizes[i] - o)}); cnt++; }
+      if (cnt == 0) { wpieces.push_back({i, 0, 0}); cnt = 1; }
+      remaining[i] = cnt;
+    }
+    parallel_for(wpieces.size(), io_threads, [&](size_t k) {
+      const Piece &pc = wpieces[k];
+      const uint32_t i = pc.file;
+      if (pc.len && !write_piece(tmp_path[i].c_str(), ctx->h_tree_out + out_off[i] + pc.off, pc.off, pc.len)) piece_fail[i]++;
+      if (--remaining[i] == 0) {
+        bool ok = piece_fail[i] == 0 && chmod(tmp_path[i].c_str(), files[i].mode & 07777) == 0 &&
+                  rename(tmp_path[i].c_str(), files[i].path.c_str()) == 0;
+        if (ok) { n_gpu++; in_b += sizes[i]; out_b += out_sizes[i]; }
+        else { unlink(tmp_path[i].c_str()); n_failed++; }
+      }
     });
   } else {
     for (uint32_t i = 0; i < n; i++) if (status[i] == LB2_ST_OK) { n_gpu++; in_b += sizes[i]; out_b += out_sizes[i]; }

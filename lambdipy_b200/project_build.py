@@ -56,7 +56,24 @@ def strip_build_tree(build_directory, backend=None):
                     fallback_host_strip=True)
     print("Stripped %d shared objects on the GPU (%d via host strip), %.1f MB -> %.1f MB" %
           (st["n_gpu"], st["n_fallback"], st["in_bytes"] / 1e6, st["out_bytes"] / 1e6))
+    print(bundle_report(build_directory))
     return XARGS_FAILURE_RC if st["n_failed"] else 0
+
+
+LAMBDA_UNZIPPED_LIMIT = 250 * 1024 * 1024  # the limit the reference exists to meet (/root/reference/README.md:4-5)
+
+
+def bundle_report(build_directory):
+    """Size of the finished bundle against Lambda's 250 MB unzipped limit (the reference's README
+    promises 'tips to further improve your bundle size' as a TODO, README.md:23)."""
+    total = 0
+    for d, _, fs in os.walk(build_directory):
+        for f in fs:
+            p = os.path.join(d, f)
+            if not os.path.islink(p):
+                total += os.path.getsize(p)
+    pct = 100.0 * total / LAMBDA_UNZIPPED_LIMIT
+    return "Bundle size: %.1f MB = %.0f %% of the 250 MB Lambda limit%s" % (total / 1e6, pct, "" if pct <= 100 else "  ** over the limit **")
 
 
 def install_non_resolved_requirements(resolved_requirements, requirements, python_version, keep_tests=None, no_docker=False,

@@ -69,6 +69,14 @@ VARIANTS = {
     "c_split_dwarf_types": ("c", ["-shared", "-fPIC", "-O1", "-g", "-fdebug-types-section"]),
     "c_dwarf4": ("c", ["-shared", "-fPIC", "-O1", "-gdwarf-4"]),
     "c_Os_unwind": ("c", ["-shared", "-fPIC", "-Os", "-g", "-fasynchronous-unwind-tables"]),
+    "c_static": ("c", ["-static", "-O1", "-g"]),
+    "c_static_pie": ("c", ["-static-pie", "-O1"]),
+    "c_relr": ("c", ["-shared", "-fPIC", "-g", "-Wl,-z,pack-relative-relocs"]),
+    "c_ibt_shstk": ("c", ["-shared", "-fPIC", "-g", "-fcf-protection=full", "-Wl,-z,ibt,-z,shstk"]),
+    "c_zlib_gnu_debug": ("c", ["-shared", "-fPIC", "-g", "-Wl,--compress-debug-sections=zlib-gnu"]),
+    "c_text_segment": ("c", ["-shared", "-fPIC", "-g", "-Wl,-Ttext-segment=0x400000"]),
+    "c_sep_loadable": ("c", ["-shared", "-fPIC", "-g", "-Wl,-z,separate-loadable-segments"]),
+    "c_bsymbolic_noplt": ("c", ["-shared", "-fPIC", "-g", "-O2", "-fno-plt", "-Wl,-Bsymbolic", "-Wl,-z,nocombreloc"]),
     "cxx_plain": ("cxx", ["-shared", "-fPIC", "-O1"]),
     "cxx_g": ("cxx", ["-shared", "-fPIC", "-O0", "-g"]),
     "cxx_gold_g": ("cxx", ["-shared", "-fPIC", "-O1", "-g", "-fuse-ld=gold"]),
