@@ -528,27 +528,6 @@ static bool write_piece(const char *tmp, const uint8_t *src, uint64_t off, uint6
   return ok;
 }
 
-// temp file in the same directory + rename, mode preserved (what strip does; mtime is not kept)
-[[maybe_unused]] static bool replace_file(const std::string &p, const uint8_t *src, uint64_t n, mode_t mode) {
-  std::string tmp = p + ".lb2XXXXXX";
-  std::vector<char> t(tmp.begin(), tmp.end());
-  t.push_back(0);
-  int fd = mkstemp(t.data());
-  if (fd < 0) return false;
-  uint64_t put = 0;
-  bool ok = true;
-  while (put < n) {
-    ssize_t r = write(fd, src + put, n - put);
-    if (r <= 0) { if (r < 0 && errno == EINTR) continue; ok = false; break; }
-    put += (uint64_t)r;
-  }
-  if (ok && fchmod(fd, mode & 07777) != 0) ok = false;
-  close(fd);
-  if (ok && rename(t.data(), p.c_str()) != 0) ok = false;
-  if (!ok) unlink(t.data());
-  return ok;
-}
-
 static int host_strip(const std::string &p) {
   const char *argv[] = {"strip", p.c_str(), nullptr};
   pid_t pid;
