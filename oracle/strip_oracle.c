@@ -388,6 +388,49 @@ static int sec_in_seg(const Shdr *s, const Phdr *p) {
   return 1;
 }
 
+/* ---------------------------------------------------------------- conservative input gate
+ * BFD normalises a number of header fields from its own tables (section type and flags by NAME,
+ * sh_link by name lookup of .dynstr/.dynsym, LMA from p_paddr, ...).  On files written by ld, gold,
+ * lld, patchelf or objcopy those fields already hold BFD's values, so the rules above never see the
+ * difference.  Anything that deviates is declared out of contract (LBO_UNSUPPORTED_LAYOUT -> the
+ * product hands the file to the host strip) instead of being guessed at.  Found with
+ * oracle/fuzz_vs_gnu.py. */
+static int name_is(const char *n, const char *base) {   /* "base" or "base.*" (BFD prefix entries with -2) */
+  size_t l = strlen(base);
+  return strncmp(n, base, l) == 0 && (n[l] == 0 || n[l] == '.');
+}
+static int expected_type_by_name(const char *n) {  /* bfd/elf.c special_sections_*; -1: not a special name */
+  if (name_is(n, ".bss") || name_is(n, ".tbss") || name_is(n, ".sbss") || name_is(n, ".lbss") || has_prefix(n, ".gnu.linkonce.b") || name_is(n, ".noinit")) return SHT_NOBITS;
+  if (strcmp(n, ".comment") == 0 || name_is(n, ".data") || name_is(n, ".data1") || has_prefix(n, ".debug") || strcmp(n, ".fini") == 0 ||
+      strcmp(n, ".got") == 0 || strcmp(n, ".init") == 0 || strcmp(n, ".interp") == 0 || has_prefix(n, ".line") || strcmp(n, ".plt") == 0 ||
+      name_is(n, ".rodata") || name_is(n, ".rodata1") || name_is(n, ".tdata") || name_is(n, ".text") || name_is(n, ".sdata") ||
+      name_is(n, ".ldata") || name_is(n, ".lrodata") || name_is(n, ".persistent") || has_prefix(n, ".gnu.linkonce.wi."))
+    return SHT_PROGBITS;
+  if (strcmp(n, ".dynamic") == 0) return 6;
+  if (strcmp(n, ".dynstr") == 0 || strcmp(n, ".strtab") == 0 || strcmp(n, ".shstrtab") == 0) return SHT_STRTAB;
+  if (strcmp(n, ".dynsym") == 0) return SHT_DYNSYM;
+  if (strcmp(n, ".symtab") == 0) return SHT_SYMTAB;
+  if (name_is(n, ".fini_array")) return 15;
+  if (name_is(n, ".init_array")) return 14;
+  if (name_is(n, ".preinit_array")) return 16;
+  if (strcmp(n, ".gnu.version") == 0) return 0x6fffffff;
+  if (strcmp(n, ".gnu.version_d") == 0) return 0x6ffffffd;
+  if (strcmp(n, ".gnu.version_r") == 0) return 0x6ffffffe;
+  if (strcmp(n, ".gnu.hash") == 0) return 0x6ffffff6;
+  if (strcmp(n, ".hash") == 0) return 5;
+  if (has_prefix(n, ".note")) return SHT_NOTE;
+  if (has_prefix(n, ".rela")) return SHT_RELA;
+  if (name_is(n, ".rel")) return SHT_REL;   /* on RELA targets BFD matches ".rel" only as "rel" or "rel.*" (not .relro_padding, .relr.dyn) */
+  return -1;
+}
+static int type_is_known(uint32_t t) {
+  switch (t) {
+    case SHT_PROGBITS: case SHT_SYMTAB: case SHT_STRTAB: case SHT_RELA: case 5: case 6: case SHT_NOTE: case SHT_NOBITS: case SHT_DYNSYM:
+    case 14: case 15: case 16: case 19 /* SHT_RELR */: case 0x6ffffff6: case 0x6ffffffd: case 0x6ffffffe: case 0x6fffffff: case 0x70000001: return 1;
+    default: return 0;
+  }
+}
+
 int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, unsigned flags) {
   *out_p = NULL;
   *out_n = 0;
@@ -430,6 +473,9 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
         (S[i].h.sh_offset > n || S[i].h.sh_size > n - S[i].h.sh_offset)) { rc = LBO_MALFORMED; goto done; }
   }
 
+  for (uint64_t j = 0; j < phnum; j++)   /* gate: section LMAs come from p_paddr; Linux objects have paddr == vaddr */
+    if (P[j].p_paddr != P[j].p_vaddr) UNSUP();
+
   /* R1 */
   for (uint64_t i = 1; i < shnum; i++) {
     const Shdr *h = &S[i].h;
@@ -443,6 +489,42 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
     if ((h->sh_type == SHT_DYNSYM || h->sh_type == SHT_SYMTAB || h->sh_type == SHT_RELA) && h->sh_entsize != 24) UNSUP();
     if (h->sh_type == 0x6fffffff && h->sh_entsize != 2) UNSUP();
     if (!alloc && (h->sh_type == SHT_REL || h->sh_type == SHT_RELA)) UNSUP();
+    /* ---- gate (see above) */
+    {
+      const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;
+      const char *nm = S[i].name;
+      int want = expected_type_by_name(nm);
+      if (h->sh_flags & ~ALLOWED) UNSUP();
+      if (!type_is_known(h->sh_type)) UNSUP();
+      if (h->sh_type == SHT_NOBITS && !alloc) UNSUP();
+      if (want >= 0 && (uint32_t)want != h->sh_type && !(h->sh_type == 0x70000001 && want == SHT_PROGBITS)) UNSUP();
+      if ((h->sh_flags & SHF_INFO_LINK) && h->sh_type != SHT_RELA && h->sh_type != SHT_REL) UNSUP();
+      if (h->sh_link >= shnum) UNSUP();
+      switch (h->sh_type) {
+        case SHT_DYNSYM: case 6: case 0x6ffffffd: case 0x6ffffffe:   /* BFD: sh_link := index of ".dynstr" */
+          if (h->sh_link == 0 || strcmp(S[h->sh_link].name, ".dynstr") != 0) UNSUP();
+          if (h->sh_type == 6 && h->sh_info != 0) UNSUP();
+          if (h->sh_type == SHT_DYNSYM && (h->sh_size % 24 != 0 || h->sh_info > h->sh_size / 24)) UNSUP(); /* BFD refuses */
+          break;
+        case 5: case 0x6ffffff6: case 0x6fffffff:                     /* BFD: sh_link := index of ".dynsym" */
+          if (h->sh_link == 0 || strcmp(S[h->sh_link].name, ".dynsym") != 0 || h->sh_info != 0) UNSUP();
+          break;
+        case SHT_RELA: case SHT_REL:
+          if (h->sh_link != 0 && strcmp(S[h->sh_link].name, ".dynsym") != 0) UNSUP();
+          if (h->sh_info >= shnum) UNSUP();
+          break;
+        case SHT_SYMTAB:                                              /* dropped, but BFD reads it first and refuses a broken one */
+          if (h->sh_link == 0 || S[h->sh_link].h.sh_type != SHT_STRTAB || (S[h->sh_link].h.sh_flags & SHF_ALLOC)) UNSUP();
+          if (h->sh_size % 24 != 0 || h->sh_info > h->sh_size / 24) UNSUP();
+          break;
+        case SHT_STRTAB:
+          if (h->sh_link != 0 || h->sh_info != 0) UNSUP();
+          break;
+        default:                                                      /* ordinary sections: BFD writes 0/0 */
+          if (h->sh_link != 0 || h->sh_info != 0) UNSUP();
+          break;
+      }
+    }
     S[i].keep = !drop;
     /* BFD keeps alignment as a power of two that the section address honours
      * (probe: doctored sh_addralign 0/3/24/4096 -> min(lowbit(align), lowbit(addr)), 0 -> 1). */
@@ -584,6 +666,20 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
       if (S[i].h.sh_type != SHT_NOBITS) last_bits = (int64_t)i;
     }
     if (t == PT_GNU_STACK) { NP[j].p_offset = 0; NP[j].p_filesz = 0; continue; }
+    if (first >= 0 && t != PT_GNU_RELRO && t != PT_TLS) {
+      /* gate: a segment that carries sections must describe exactly their extent (BFD recomputes
+       * offset/filesz/memsz from the sections; natural files already agree) */
+      uint64_t aend = 0, fend = 0;
+      int any_alloc = 0;
+      for (uint64_t i = 1; i < shnum; i++) {
+        if (!S[i].keep || !sec_in_seg(&in_hdr[i], &P[j])) continue;
+        if (in_hdr[i].sh_flags & SHF_ALLOC) { any_alloc = 1; if (in_hdr[i].sh_addr + in_hdr[i].sh_size > aend) aend = in_hdr[i].sh_addr + in_hdr[i].sh_size; }
+        if (in_hdr[i].sh_type != SHT_NOBITS && in_hdr[i].sh_offset + in_hdr[i].sh_size > fend) fend = in_hdr[i].sh_offset + in_hdr[i].sh_size;
+      }
+      if (any_alloc && (in_hdr[first].sh_addr != P[j].p_vaddr || aend - P[j].p_vaddr != P[j].p_memsz)) UNSUP();
+      if (in_hdr[first].sh_type != SHT_NOBITS && in_hdr[first].sh_offset != P[j].p_offset) UNSUP();
+      if (fend && fend - P[j].p_offset != P[j].p_filesz) UNSUP();
+    }
     if (t == PT_GNU_RELRO) {
       int ok = 0;
       if (first >= 0) {
@@ -697,6 +793,10 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
     if (h.sh_link && h.sh_link < shnum) h.sh_link = S[h.sh_link].keep ? (uint32_t)S[h.sh_link].new_index : 0;
     if ((h.sh_flags & SHF_INFO_LINK) && h.sh_info && h.sh_info < shnum)
       h.sh_info = S[h.sh_info].keep ? (uint32_t)S[h.sh_info].new_index : 0;
+    if ((h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && s->h.sh_link == 0) {
+      /* assign_section_numbers(): an allocated reloc section without a symbol table gets .dynsym */
+      for (int q = 1; q < nk; q++) if (strcmp(S[order[q]].name, ".dynsym") == 0) { h.sh_link = (uint32_t)q; break; }
+    }
     if (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) {
       /* BFD re-derives the section a dynamic reloc section applies to from its NAME
        * (elf.c: elf_get_reloc_section / _bfd_elf_plt_get_reloc_section): strip ".rel[a]",
@@ -716,12 +816,15 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
           for (int q = 1; q < nk; q++) if (strcmp(S[order[q]].name, t) == 0) { target = q; break; }
         }
       }
+      /* SHF_INFO_LINK and sh_info exist in the output exactly when BFD finds the target section */
+      h.sh_flags &= ~(uint64_t)SHF_INFO_LINK;
+      h.sh_info = 0;
       if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
     }
     /* elf.c elf_fake_sections(): BFD recomputes sh_entsize for the section types it knows
      * (probe: doctored sh_entsize on each section of a gcc-built .so, binutils 2.42). */
     switch (h.sh_type) {
-      case 14: case 15: case 16: h.sh_entsize = 8; break;          /* INIT/FINI/PREINIT_ARRAY */
+      case 14: case 15: case 16: case 19: h.sh_entsize = 8; break;  /* INIT/FINI/PREINIT_ARRAY, RELR */
       case 5: h.sh_entsize = 4; break;                              /* SHT_HASH (x86-64/aarch64) */
       case 6: h.sh_entsize = 16; break;                             /* SHT_DYNAMIC */
       case 0x6ffffff6: h.sh_entsize = 0; break;                     /* SHT_GNU_HASH, 64-bit */
