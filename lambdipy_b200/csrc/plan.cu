@@ -123,6 +123,49 @@ __device__ bool is_debug_name(const char *n) {
          d_prefix(n, ".gnu.linkonce.wi.") || d_prefix(n, ".line") || d_prefix(n, ".stab") || d_streq(n, ".gdb_index");
 }
 
+// ---- conservative input gate ------------------------------------------------------------------
+// BFD normalises several header fields from its own tables (section type and flags by NAME, sh_link by
+// looking up .dynstr/.dynsym, LMA from p_paddr ...).  Files written by ld, gold, lld, patchelf or
+// objcopy already hold BFD's values; anything else is reported LB2_ST_UNSUPPORTED_LAYOUT (-> host
+// strip) rather than guessed at.  Mirrors the gate of the test oracle; found by structure fuzzing.
+__device__ bool name_is(const char *n, const char *base) {  // "base" or "base.*"
+  int l = 0;
+  for (; base[l]; l++) if (n[l] != base[l]) return false;
+  return n[l] == 0 || n[l] == '.';
+}
+__device__ int expected_type_by_name(const char *n) {  // bfd/elf.c special_sections_*; -1: not a special name
+  if (name_is(n, ".bss") || name_is(n, ".tbss") || name_is(n, ".sbss") || name_is(n, ".lbss") || d_prefix(n, ".gnu.linkonce.b") || name_is(n, ".noinit")) return SHT_NOBITS;
+  if (d_streq(n, ".comment") || name_is(n, ".data") || name_is(n, ".data1") || d_prefix(n, ".debug") || d_streq(n, ".fini") || d_streq(n, ".got") ||
+      d_streq(n, ".init") || d_streq(n, ".interp") || d_prefix(n, ".line") || d_streq(n, ".plt") || name_is(n, ".rodata") || name_is(n, ".rodata1") ||
+      name_is(n, ".tdata") || name_is(n, ".text") || name_is(n, ".sdata") || name_is(n, ".ldata") || name_is(n, ".lrodata") || name_is(n, ".persistent") ||
+      d_prefix(n, ".gnu.linkonce.wi."))
+    return SHT_PROGBITS;
+  if (d_streq(n, ".dynamic")) return SHT_DYNAMIC;
+  if (d_streq(n, ".dynstr") || d_streq(n, ".strtab") || d_streq(n, ".shstrtab")) return SHT_STRTAB;
+  if (d_streq(n, ".dynsym")) return SHT_DYNSYM;
+  if (d_streq(n, ".symtab")) return SHT_SYMTAB;
+  if (name_is(n, ".fini_array")) return SHT_FINI_ARRAY;
+  if (name_is(n, ".init_array")) return SHT_INIT_ARRAY;
+  if (name_is(n, ".preinit_array")) return SHT_PREINIT_ARRAY;
+  if (d_streq(n, ".gnu.version")) return (int)SHT_GNU_VERSYM;
+  if (d_streq(n, ".gnu.version_d")) return (int)SHT_GNU_VERDEF;
+  if (d_streq(n, ".gnu.version_r")) return (int)SHT_GNU_VERNEED;
+  if (d_streq(n, ".gnu.hash")) return (int)SHT_GNU_HASH;
+  if (d_streq(n, ".hash")) return SHT_HASH;
+  if (d_prefix(n, ".note")) return SHT_NOTE;
+  if (d_prefix(n, ".rela")) return SHT_RELA;
+  if (name_is(n, ".rel")) return SHT_REL;
+  return -1;
+}
+__device__ bool type_is_known(uint32_t t) {
+  switch (t) {
+    case SHT_PROGBITS: case SHT_SYMTAB: case SHT_STRTAB: case SHT_RELA: case SHT_HASH: case SHT_DYNAMIC: case SHT_NOTE: case SHT_NOBITS:
+    case SHT_DYNSYM: case SHT_INIT_ARRAY: case SHT_FINI_ARRAY: case SHT_PREINIT_ARRAY: case 19 /* SHT_RELR */: case SHT_GNU_HASH:
+    case SHT_GNU_VERDEF: case SHT_GNU_VERNEED: case SHT_GNU_VERSYM: case 0x70000001u /* SHT_X86_64_UNWIND */: return true;
+    default: return false;
+  }
+}
+
 // BFD ELF_SECTION_IN_SEGMENT (check_vma, !strict): which sections a program header carries.
 __device__ bool sec_in_seg(const Shdr &s, const Phdr &p) {
   const uint32_t t = p.p_type;
@@ -532,6 +575,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   // ---- C. R1 keep/drop mask, lane i <-> sections i and i+32; verdicts combined by ballot
   {
     int err_mal = 0, err_uns = 0;
+    if (lane < phnum && sm.ph[lane].p_paddr != sm.ph[lane].p_vaddr) err_uns = 1;  // gate: section LMAs come from p_paddr
     for (int i = lane; i < shnum; i += 32) {
       Shdr &h = sm.sh[i];
       sm.keep[i] = 0; sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
@@ -550,6 +594,41 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
       if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
       if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
+      {  // ---- gate (see expected_type_by_name)
+        const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;
+        const int want = expected_type_by_name(nm);
+        if (h.sh_flags & ~ALLOWED) err_uns = 1;
+        if (!type_is_known(h.sh_type)) err_uns = 1;
+        if (h.sh_type == SHT_NOBITS && !alloc) err_uns = 1;
+        if (want >= 0 && (uint32_t)want != h.sh_type && !(h.sh_type == 0x70000001u && want == (int)SHT_PROGBITS)) err_uns = 1;
+        if ((h.sh_flags & SHF_INFO_LINK) && h.sh_type != SHT_RELA && h.sh_type != SHT_REL) err_uns = 1;
+        if (h.sh_link >= (uint32_t)shnum) err_uns = 1;
+        else {
+          const Shdr &lk = sm.sh[h.sh_link];
+          const char *lname = lk.sh_name < strsz ? sm.names + lk.sh_name : "";
+          switch (h.sh_type) {
+            case SHT_DYNSYM: case SHT_DYNAMIC: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED:  // BFD: sh_link := index of .dynstr
+              if (h.sh_link == 0 || !d_streq(lname, ".dynstr")) err_uns = 1;
+              if (h.sh_type == SHT_DYNAMIC && h.sh_info != 0) err_uns = 1;
+              if (h.sh_type == SHT_DYNSYM && (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24)) err_uns = 1;
+              break;
+            case SHT_HASH: case SHT_GNU_HASH: case SHT_GNU_VERSYM:                         // BFD: sh_link := index of .dynsym
+              if (h.sh_link == 0 || !d_streq(lname, ".dynsym") || h.sh_info != 0) err_uns = 1;
+              break;
+            case SHT_RELA: case SHT_REL:
+              if (h.sh_link != 0 && !d_streq(lname, ".dynsym")) err_uns = 1;
+              if (h.sh_info >= (uint32_t)shnum) err_uns = 1;
+              break;
+            case SHT_SYMTAB:  // dropped, but BFD reads it first and refuses a broken one
+              if (h.sh_link == 0 || lk.sh_type != SHT_STRTAB || (lk.sh_flags & SHF_ALLOC)) err_uns = 1;
+              if (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24) err_uns = 1;
+              break;
+            default:          // ordinary sections (and string tables): BFD writes sh_link = sh_info = 0
+              if (h.sh_link != 0 || h.sh_info != 0) err_uns = 1;
+              break;
+          }
+        }
+      }
       sm.keep[i] = drop ? 0 : 1;
       // BFD keeps a power-of-two alignment the address honours: min(lowbit(align), lowbit(addr))
       uint64_t al = h.sh_addralign ? lowbit(h.sh_addralign) : 1;
@@ -713,6 +792,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
 
   LB2_T(8);
   // ---- H. R12: every other program header, one per lane
+  int gate_fail = 0;
   if (lane < phnum && sm.pkeep[lane] && sm.ph[lane].p_type != PT_LOAD) {
     const int j = lane;
     const Phdr &p = sm.ph[j];
@@ -722,10 +802,22 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       q.p_filesz = q.p_memsz = (uint64_t)new_phnum * 56;
     } else {
       int first = -1, last_bits = -1;
+      uint64_t aend = 0, fend = 0;
+      bool any_alloc = false;
       for (int i = 1; i < shnum; i++) {
-        if (!sm.keep[i] || !sec_in_seg(sm.sh[i], p)) continue;
+        const Shdr &h = sm.sh[i];
+        if (!sm.keep[i] || !sec_in_seg(h, p)) continue;
         if (first < 0) first = i;
-        if (sm.sh[i].sh_type != SHT_NOBITS) last_bits = i;
+        if (h.sh_type != SHT_NOBITS) { last_bits = i; if (h.sh_offset + h.sh_size > fend) fend = h.sh_offset + h.sh_size; }
+        if (h.sh_flags & SHF_ALLOC) { any_alloc = true; if (h.sh_addr + h.sh_size > aend) aend = h.sh_addr + h.sh_size; }
+      }
+      if (first >= 0 && t != PT_GNU_STACK && t != PT_GNU_RELRO && t != PT_TLS) {
+        // gate: a segment that carries sections must describe exactly their extent (BFD recomputes
+        // offset / filesz / memsz from the sections; natural files already agree)
+        const Shdr &hf = sm.sh[first];
+        if (any_alloc && (hf.sh_addr != p.p_vaddr || aend - p.p_vaddr != p.p_memsz)) gate_fail = 1;
+        if (hf.sh_type != SHT_NOBITS && hf.sh_offset != p.p_offset) gate_fail = 1;
+        if (fend && fend - p.p_offset != p.p_filesz) gate_fail = 1;
       }
       if (t == PT_GNU_STACK) { q.p_offset = 0; q.p_filesz = 0; }
       else if (t == PT_GNU_RELRO) {
@@ -780,6 +872,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   __syncwarp();
 
   LB2_T(9);
+  if (__ballot_sync(0xffffffffu, gate_fail)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
   // ---- I. R4 non-alloc sections packed behind the last allocated byte (align-then-add chain)
   if (lane == 0) {
     uint64_t cur = sm.cur;
@@ -893,6 +986,13 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       if (h.sh_link && h.sh_link < (uint32_t)shnum) h.sh_link = sm.keep[h.sh_link] ? sm.new_index[h.sh_link] : 0;
       if ((h.sh_flags & SHF_INFO_LINK) && h.sh_info && h.sh_info < (uint32_t)shnum)
         h.sh_info = sm.keep[h.sh_info] ? sm.new_index[h.sh_info] : 0;
+      if ((h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && sm.sh[i].sh_link == 0) {
+        // assign_section_numbers(): an allocated reloc section without a symbol table gets .dynsym
+        for (int q = 1; q < nk; q++) {
+          const int oi = sm.order[q];
+          if (sm.name_len[oi] == 7 && d_streq(sm.names + sm.sh[oi].sh_name, ".dynsym")) { h.sh_link = (uint32_t)q; break; }
+        }
+      }
       if (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) {
         // BFD re-derives the section a dynamic reloc section applies to from its name
         const char *t = nullptr;
@@ -916,10 +1016,13 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
             target = find_name(t);
           }
         }
+        // SHF_INFO_LINK and sh_info exist in the output exactly when BFD finds the target section
+        h.sh_flags &= ~(uint64_t)SHF_INFO_LINK;
+        h.sh_info = 0;
         if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
       }
       switch (h.sh_type) {  // elf_fake_sections(): entsize of the types BFD knows
-        case SHT_INIT_ARRAY: case SHT_FINI_ARRAY: case SHT_PREINIT_ARRAY: h.sh_entsize = 8; break;
+        case SHT_INIT_ARRAY: case SHT_FINI_ARRAY: case SHT_PREINIT_ARRAY: case 19 /* RELR */: h.sh_entsize = 8; break;
         case SHT_HASH: h.sh_entsize = 4; break;
         case SHT_DYNAMIC: h.sh_entsize = 16; break;
         case SHT_GNU_HASH: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED: h.sh_entsize = 0; break;

@@ -177,3 +177,40 @@ def test_tma_and_lsu_kernels_agree(variants, tmp_path, monkeypatch):
         with N.Context(0) as ctx:
             res[tma] = S.strip_buffers(ctx, blobs)[:2]
     assert res["0"] == res["1"]
+
+
+def test_structure_fuzz_gpu_matches_oracle_and_gnu(gpu_ctx, oracle, variants, tmp_path):
+    """mutated headers / sections (oracle/fuzz_vs_gnu.py): whenever the device planner accepts a
+    mutant its bytes equal the oracle's and GNU strip's; it accepts exactly the mutants the oracle's
+    gate accepts (modulo its shared-memory limits); it never 'strips' a file GNU strip refuses"""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fuzz_vs_gnu as Z
+    from lambdipy_b200 import _native as N
+    from lambdipy_b200 import strip as S
+    seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie", "c_many_sections")]
+    seeds += [p for p in F.real_corpus("small") if os.path.getsize(p) < 2_000_000][:20]
+    rng = random.Random(4242)
+    paths, blobs = [], []
+    for k in range(400):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        dst = str(d / "m.so")
+        if Z.mutate(rng, rng.choice(seeds), dst, str(d)) is None:
+            continue
+        paths.append(dst)
+        blobs.append(_read(dst))
+    assert len(blobs) > 250
+    outs, status, _ = S.strip_buffers(gpu_ctx, blobs)
+    n_ok = 0
+    for p, b, out, st in zip(paths, blobs, outs, status):
+        rc, want = oracle.strip(b)
+        if st == 0:
+            n_ok += 1
+            assert rc == 0 and out == want, p
+            gnu, err = F.gnu_strip_bytes(p, str(tmp_path))
+            assert gnu is not None and gnu == out, (p, err)
+        else:
+            assert rc != 0 or st == N.ST_PLANNER_LIMIT, (p, st, rc)
+    assert n_ok > 100
