@@ -142,3 +142,34 @@ def test_synthetic_corpus_is_valid_and_matches(oracle, tmp_path):
         assert rc == 0 and out == gnu, i
         assert len(out) < len(data)
     assert kinds == {"tiny", "compact", "sepcode"}
+
+
+def test_structure_fuzz_against_gnu_strip(oracle, variants, tmp_path):
+    """doctored header fields / objcopy-edited sections: the oracle either matches the real binary
+    byte for byte or declares the mutant out of contract -- never a silent difference, and never an
+    accepted file that GNU strip refuses (see oracle/fuzz_vs_gnu.py, which found the input gate)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fuzz_vs_gnu as Z
+    seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
+    seeds += [p for p in F.real_corpus("small") if os.path.getsize(p) < 1_000_000][:10]
+    rng = random.Random(99)
+    n_ok = n_unsup = 0
+    for k in range(160):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        dst = str(d / "m.so")
+        desc = Z.mutate(rng, rng.choice(seeds), dst, str(d))
+        if desc is None:
+            continue
+        data = _read(dst)
+        gnu, err = F.gnu_strip_bytes(dst, str(d))
+        rc, out = oracle.strip(data)
+        if gnu is None:
+            assert rc != 0, ("oracle accepts a file GNU strip refuses", desc, err)
+        elif rc == 0:
+            assert out == gnu, desc
+            n_ok += 1
+        else:
+            n_unsup += 1
+    assert n_ok > 50 and n_unsup > 5
