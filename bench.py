@@ -420,7 +420,7 @@ def run_b200(a, rank, local_rank, world):
                     "staged": {"value": tot_in / 1e9 / (staged_ms / e2e_steps / 1e3), "ms_per_step": staged_ms / e2e_steps,
                                "h2d_bytes_per_step": int(tot_span), "d2h_bytes_per_step": int(tot_out),
                                "api": "LB2_HOST_ZEROCOPY=0: cudaMemcpyAsync of whole files in 256 MB chunks on 3 streams"}},
-            "gpu_launches": 3 * a.steps,
+            "gpu_launches": 4 * a.steps,  # plan (2 variants), scan, compaction per step
             "clocks": clocks,
         }
         if cpu:
