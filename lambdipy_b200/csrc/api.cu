@@ -122,8 +122,11 @@ static int ws_reserve(lb2_ctx *ctx, Workspace &w, uint32_t n_files, uint64_t n_t
   return LB2_OK;
 }
 
+// Upper bound on the tiles a batch can emit: an extent of l bytes yields at most l / TILE + 2 tiles, a
+// file has at most MAX_EXT extents, and re-laid-out files may grow (LOAD alignment padding) -- 1 GB of
+// growth per batch is allowed for before the plan kernel reports overflow.
 static uint64_t tile_bound(const uint64_t *sizes, uint32_t n) {
-  uint64_t t = 0;
+  uint64_t t = 65536;
   for (uint32_t i = 0; i < n; i++) t += sizes[i] / TILE_BYTES + 2 * MAX_EXT + 16;
   return t;
 }
