@@ -1143,6 +1143,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
 }
 
+#ifndef LB2_HOST_EMULATION  // (the CPU warp emulator under tests/emu compiles only the plan kernel)
 // ---------------------------------------------------------------- output offsets
 // Exclusive scan of the 256-byte-rounded output sizes: where each stripped file starts in the
 // output arena.  One CTA; n_files is at most a few 10^5.
@@ -1191,5 +1192,7 @@ void launch_plan(const PlanArgs &a, cudaStream_t s) {
 void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, cudaStream_t s) {
   lb2_scan_kernel<<<1, 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr);
 }
+
+#endif  // LB2_HOST_EMULATION
 
 }  // namespace lb2

@@ -1,0 +1,111 @@
+// plan_emu.cpp -- TEST HARNESS: runs the PRODUCT's device planner source (lambdipy_b200/csrc/plan.cu) on the
+// CPU by emulating one warp with 32 host threads (barrier-based __syncwarp / __ballot_sync / __shfl*), then
+// executes the emitted tile list with memcpy to materialise the stripped file.  It lets the CPU test-suite
+// (-m "not gpu") check the planner logic that ships in the CUDA library against the oracle and GNU strip
+// without a GPU.  It is NOT a CPU fallback: it lives under tests/, is built only by the tests, is never
+// imported by lambdipy_b200/, and emulates a single file per call at kHz speeds.
+#include <atomic>
+#include <barrier>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+#include "cuda_runtime.h"  // the shim
+
+// ---- warp emulation state
+static thread_local uint3 threadIdx, blockIdx;
+static std::barrier<> *g_bar;
+static uint64_t g_xchg[32];
+static inline void __syncwarp() { g_bar->arrive_and_wait(); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  g_xchg[threadIdx.x] = pred ? 1 : 0;
+  g_bar->arrive_and_wait();
+  unsigned m = 0;
+  for (int i = 0; i < 32; i++) m |= (unsigned)g_xchg[i] << i;
+  g_bar->arrive_and_wait();
+  return m;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+  uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
+  g_xchg[threadIdx.x] = raw;
+  g_bar->arrive_and_wait();
+  T r; memcpy(&r, &g_xchg[src & 31], sizeof r);
+  g_bar->arrive_and_wait();
+  return r;
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+  uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
+  g_xchg[threadIdx.x] = raw;
+  g_bar->arrive_and_wait();
+  T r = v;
+  if ((int)threadIdx.x >= d) memcpy(&r, &g_xchg[threadIdx.x - d], sizeof r);
+  g_bar->arrive_and_wait();
+  return r;
+}
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline long long clock64() { return 0; }
+
+#define LB2_HOST_EMULATION 1
+#include "../../lambdipy_b200/csrc/plan.cu"
+
+using namespace lb2;
+
+template <int NB, int NN, bool RETRY> static void run_warp(const PlanArgs &a) {
+  std::barrier<> bar(32);
+  g_bar = &bar;
+  std::vector<std::thread> th;
+  for (int l = 0; l < 32; l++)
+    th.emplace_back([&, l] {
+      threadIdx = uint3{(uint32_t)l, 0, 0};
+      blockIdx = uint3{0, 0, 0};
+      lb2_plan_kernel<NB, NN, RETRY>(a);
+      bar.arrive_and_drop();  // lanes leave together (all early exits in the kernel are warp-uniform)
+    });
+  for (auto &t : th) t.join();
+}
+
+extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8_t **out_p, uint64_t *out_n) {
+  *out_p = nullptr; *out_n = 0;
+  // 256-aligned private copy, as the arena contract requires
+  const uint64_t cap = ((n + 255) & ~255ull) + 256;
+  uint8_t *arena = static_cast<uint8_t *>(aligned_alloc(256, cap));
+  memset(arena, 0, cap);
+  memcpy(arena, in, n);
+  uint8_t *scratch = static_cast<uint8_t *>(aligned_alloc(256, SCR_STRIDE));
+  memset(scratch, 0, SCR_STRIDE);
+  const uint64_t tile_cap = n / TILE_BYTES + 2 * MAX_EXT + 16 + 4096;
+  std::vector<Tile> tiles(tile_cap);
+  uint64_t in_off = 0, in_size = n, out_size = 0;
+  int32_t status = -99;
+  BatchCounters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  PlanArgs a;
+  a.in = arena; a.in_off = &in_off; a.in_size = &in_size; a.n_files = 1; a.flags = flags;
+  a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr;
+  run_warp<1024, 52, false>(a);
+  if (status == ST_RETRY_BIG_NOTES) run_warp<MAX_NOTE_BYTES, MAX_NOTES, true>(a);
+  int rc = status;
+  if (status == ST_OK && !ctr.overflow) {
+    uint8_t *out = static_cast<uint8_t *>(malloc(out_size ? out_size : 1));
+    memset(out, 0xA5, out_size);  // poison: every byte must be produced by exactly one tile
+    std::vector<uint8_t> hit(out_size, 0);
+    for (unsigned long long t = 0; t < ctr.n_tiles; t++) {
+      const Tile &tl = tiles[t];
+      if (tl.dst_rel + tl.len > out_size) { rc = -1000; break; }
+      if (tl.src) memcpy(out + tl.dst_rel, reinterpret_cast<const void *>(tl.src), tl.len);
+      else memset(out + tl.dst_rel, 0, tl.len);
+      for (uint32_t q = 0; q < tl.len; q++) hit[tl.dst_rel + q]++;
+    }
+    for (uint64_t q = 0; q < out_size && rc == 0; q++) if (hit[q] != 1) rc = -1001;  // gap or double write
+    if (rc == 0) { *out_p = out; *out_n = out_size; } else free(out);
+  }
+  free(arena); free(scratch);
+  return rc;
+}
+extern "C" void lb2emu_free(uint8_t *p) { free(p); }

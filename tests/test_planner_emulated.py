@@ -1,0 +1,96 @@
+"""CPU checks of the PRODUCT's device planner (lambdipy_b200/csrc/plan.cu) without a GPU: the kernel
+source is compiled with g++ and one warp is emulated by 32 host threads (tests/emu/plan_emu.cpp);
+the emitted tile list is executed with memcpy and must tile the output exactly.  The result is
+compared with the oracle and with the real GNU strip.  This is a TEST HARNESS (the package never
+loads it); the GPU parity tests remain the gate for the compiled CUDA library."""
+import os
+import random
+
+import pytest
+
+import elf_fixtures as F
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu_lib
+    return emu_lib.load()
+
+
+def _read(p):
+    with open(p, "rb") as f:
+        return f.read()
+
+
+def _agree(emu, oracle, data, no_merge=False):
+    rc, want = oracle.strip(data, no_merge)
+    st, got = emu.strip(data, no_merge)
+    if st == 0:
+        assert rc == 0 and got == want
+    else:
+        assert st > -1000, "tile list does not cover the output exactly once"
+        assert rc != 0 or st == 8  # 8 = LB2_ST_PLANNER_LIMIT (shared-memory limits of the device planner)
+    return st
+
+
+def test_golden_vectors(emu):
+    for f in sorted(os.listdir(GOLDEN)):
+        if f.endswith(".in.bin"):
+            st, got = emu.strip(_read(os.path.join(GOLDEN, f)))
+            assert st == 0 and got == _read(os.path.join(GOLDEN, f.replace(".in.bin", ".gnu.bin"))), f
+
+
+@pytest.mark.parametrize("no_merge", [False, True])
+def test_variants_notes_edges(emu, oracle, variants, note_files, doctored, no_merge):
+    n_ok = 0
+    for name, p in {**variants, **note_files, **doctored}.items():
+        if name == "c_maxpage_2m":
+            continue
+        st = _agree(emu, oracle, _read(p), no_merge)
+        n_ok += st == 0
+        if name == "c_many_sections":
+            assert st == 8
+    assert n_ok >= 45
+
+
+def test_random_notes_and_structure_fuzz(emu, oracle, variants, fixture_dir, tmp_path):
+    import sys
+    from test_oracle_vs_gnu_strip import _random_notes
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fuzz_vs_gnu as Z
+    rng = random.Random(5)
+    for case in range(40):
+        p = os.path.join(fixture_dir, "emu_rnd_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([3, 8, 20, 60, 150])))
+        assert _agree(emu, oracle, _read(p)) == 0
+    seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
+    accepted = 0
+    for k in range(300):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        dst = str(d / "m.so")
+        if Z.mutate(rng, rng.choice(seeds), dst, str(d)) is None:
+            continue
+        accepted += _agree(emu, oracle, _read(dst)) == 0
+    assert accepted > 80
+
+
+def test_real_wheels_and_gnu_strip(emu, oracle, tmp_path):
+    paths = F.real_corpus("small")
+    for p in paths:
+        data = _read(p)
+        assert _agree(emu, oracle, data) == 0, p
+    # and straight against the real binary for a few
+    for p in paths[:8]:
+        gnu, err = F.gnu_strip_bytes(p, str(tmp_path))
+        st, got = emu.strip(_read(p))
+        assert st == 0 and got == gnu, p
+
+
+def test_synthetic_corpus(emu, oracle):
+    from lambdipy_b200.corpus import Corpus
+    c = Corpus(40, seed=17, max_size=1 << 20)
+    for i in range(len(c)):
+        assert _agree(emu, oracle, c.materialize(i)) == 0
