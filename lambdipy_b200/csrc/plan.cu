@@ -43,6 +43,7 @@ struct PlanSmem {
   uint64_t src_addr[MAX_SH];  // absolute device address of the section's bytes (input or scratch)
   uint64_t ext_src[MAX_EXT], ext_dst[MAX_EXT], ext_len[MAX_EXT];
   uint32_t ext_tiles[MAX_EXT];
+  uint64_t ent_key[MAX_SH + 1];   // last 8 characters of each unique name, reversed (phase J)
   uint32_t ent_off[MAX_SH + 1];
   uint16_t ent_str[MAX_SH + 1];
   uint16_t ent_len[MAX_SH + 1];
@@ -643,7 +644,32 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   LB2_T(4);
   // ---- D. R2 output order (hoist of a later dynsym in front of the first section linking to
   //         it ... BFD: in front of the first REL/RELA that uses it) and new section indices.
-  if (lane == 0) {
+  // Common case (no hoist, every linker-native file): new index = rank among the kept sections, straight
+  // from the ballot masks.  Only files that need the hoist take the serial walk.
+  bool need_hoist;
+  uint64_t keepmask;
+  {
+    int hoist = 0;
+    for (int i = lane; i < shnum; i += 32) {
+      const Shdr &h = sm.sh[i];
+      if (sm.keep[i] && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && h.sh_link < (uint32_t)shnum && (int)h.sh_link > i &&
+          sm.keep[h.sh_link] && (sm.sh[h.sh_link].sh_type == SHT_DYNSYM || sm.sh[h.sh_link].sh_type == SHT_SYMTAB))
+        hoist = 1;
+    }
+    need_hoist = __ballot_sync(0xffffffffu, hoist) != 0;
+    const unsigned lo = __ballot_sync(0xffffffffu, lane < shnum && sm.keep[lane]);
+    const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < shnum && sm.keep[lane + 32]);
+    keepmask = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  if (!need_hoist) {
+    for (int i = lane; i < shnum; i += 32)
+      if ((keepmask >> i) & 1) {
+        const int k = __popcll(keepmask & ((1ull << i) - 1));
+        sm.new_index[i] = (uint8_t)k;
+        sm.order[k] = (uint8_t)i;
+      }
+    if (lane == 0) sm.nk = __popcll(keepmask);
+  } else if (lane == 0) {
     uint64_t emitted = 0;
     int nk = 0;
     for (int i = 0; i < shnum; i++) {
@@ -904,55 +930,103 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
   }
   __syncwarp();
-  if (lane == 0) {
-    int nent = 0;
-    sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; nent = 1;
-    for (int k = 1; k < nk; k++) {
-      const int i = sm.order[k];
-      if (sm.piece[k] == k && sm.name_len[i] != 0) {
-        sm.ent_str[nent] = (uint16_t)sm.sh[i].sh_name;
-        sm.ent_len[nent] = sm.name_len[i];
-        sm.sec_ent[i] = (uint8_t)nent;
-        nent++;
-      } else if (sm.name_len[i] == 0) {
-        sm.sec_ent[i] = 0xff;  // empty name -> sh_name 0
-      } else {
-        sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
+  // entries in insertion order: ".shstrtab", then every first occurrence of a non-empty name.  The entry
+  // index is the rank of the owner among owners (ballot + popc), no serial walk.
+  {
+    int base = 1;
+    if (lane == 0) { sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; }
+    for (int k0 = 0; k0 < nk; k0 += 32) {
+      const int k = k0 + lane;
+      bool owner = false;
+      int i = 0;
+      if (k >= 1 && k < nk) { i = sm.order[k]; owner = sm.piece[k] == k && sm.name_len[i] != 0; }
+      const unsigned m = __ballot_sync(0xffffffffu, owner);
+      if (owner) {
+        const int e = base + __popc(m & ((1u << lane) - 1));
+        sm.ent_str[e] = (uint16_t)sm.sh[i].sh_name;
+        sm.ent_len[e] = sm.name_len[i];
+        sm.sec_ent[i] = (uint8_t)e;
       }
+      base += __popc(m);
     }
-    sm.nent = nent;
+    if (lane == 0) sm.nent = base;
   }
   __syncwarp();
+  for (int k = 1 + lane; k < nk; k += 32) {
+    const int i = sm.order[k];
+    if (sm.name_len[i] == 0) sm.sec_ent[i] = 0xff;                                        // empty name -> sh_name 0
+    else if (sm.piece[k] != k) sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
+  }
   const int nent = sm.nent;
+  // reversed-suffix keys: the last 8 characters, last one most significant, zero padded -- an integer compare
+  // of two keys is elf-strtab.c's strrevcmp whenever one of the names is shorter than 8 or the keys differ
   for (int e = lane; e < nent; e += 32) {
-    int r = 0;
-    for (int o = 0; o < nent; o++)
-      if (o != e && strrev_cmp(sm.names + sm.ent_str[o], sm.ent_len[o], sm.names + sm.ent_str[e], sm.ent_len[e]) < 0) r++;
-    sm.ent_sorted[r] = (uint8_t)e;  // names are unique => ranks are a permutation
+    const char *nm = sm.names + sm.ent_str[e];
+    const int len = sm.ent_len[e];
+    uint64_t key = 0;
+    for (int q = 0; q < 8; q++) key = (key << 8) | (q < len ? (uint8_t)nm[len - 1 - q] : 0);
+    sm.ent_key[e] = key;
     sm.ent_host[e] = -1;
+  }
+  __syncwarp();
+  for (int e = lane; e < nent; e += 32) {
+    const uint64_t ke = sm.ent_key[e];
+    const int le = sm.ent_len[e];
+    int r = 0;
+    for (int o = 0; o < nent; o++) {
+      if (o == e) continue;
+      const uint64_t ko = sm.ent_key[o];
+      bool less;
+      if (ko != ke) less = ko < ke;
+      else less = strrev_cmp(sm.names + sm.ent_str[o], sm.ent_len[o], sm.names + sm.ent_str[e], le) < 0;  // both >= 8 long
+      r += less;
+    }
+    sm.ent_sorted[r] = (uint8_t)e;  // names are unique => ranks are a permutation
   }
   __syncwarp();
   if (lane == 0) {
     int cur = sm.ent_sorted[nent - 1];
-    for (int s = nent - 2; s >= 0; s--) {
-      const int c = sm.ent_sorted[s];
-      const int lc = sm.ent_len[c], lh = sm.ent_len[cur];
+    uint64_t kh = sm.ent_key[cur];
+    int lh = sm.ent_len[cur];
+    for (int s2 = nent - 2; s2 >= 0; s2--) {
+      const int c = sm.ent_sorted[s2];
+      const int lc = sm.ent_len[c];
+      const uint64_t kc = sm.ent_key[c];
       bool suffix = lh > lc;
       if (suffix) {
-        const char *hs = sm.names + sm.ent_str[cur] + (lh - lc), *cs = sm.names + sm.ent_str[c];
-        for (int q = 0; q < lc; q++) if (hs[q] != cs[q]) { suffix = false; break; }
+        if (lc <= 8) suffix = (lc == 8 ? kh == kc : (kh >> (8 * (8 - lc))) == (kc >> (8 * (8 - lc))));
+        else {
+          const char *hs = sm.names + sm.ent_str[cur] + (lh - lc), *cs = sm.names + sm.ent_str[c];
+          for (int q = 0; q < lc; q++) if (hs[q] != cs[q]) { suffix = false; break; }
+        }
       }
       if (suffix) sm.ent_host[c] = (int16_t)cur;
-      else cur = c;
+      else { cur = c; kh = kc; lh = lc; }
     }
-    uint32_t size = 1;
-    for (int e = 0; e < nent; e++) if (sm.ent_host[e] < 0) { sm.ent_off[e] = size; size += sm.ent_len[e] + 1u; }
-    for (int e = 0; e < nent; e++) if (sm.ent_host[e] >= 0) { int h = sm.ent_host[e]; sm.ent_off[e] = sm.ent_off[h] + (sm.ent_len[h] - sm.ent_len[e]); }
-    sm.new_strsz = size;
-    // R5
-    sm.shstr_off = sm.cur;
-    sm.new_shoff = align_up(sm.cur + size, 8);
-    sm.total = sm.new_shoff + (uint64_t)(nk + 1) * 64;
+  }
+  __syncwarp();
+  {
+    // offsets of the non-merged names: exclusive scan of (len + 1) in insertion order, 32 entries per step
+    uint32_t run = 1;
+    for (int e0 = 0; e0 < nent; e0 += 32) {
+      const int e = e0 + lane;
+      const uint32_t v = (e < nent && sm.ent_host[e] < 0) ? sm.ent_len[e] + 1u : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (e < nent && sm.ent_host[e] < 0) sm.ent_off[e] = run + inc - v;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    for (int e = lane; e < nent; e += 32)
+      if (sm.ent_host[e] >= 0) { const int h = sm.ent_host[e]; sm.ent_off[e] = sm.ent_off[h] + (sm.ent_len[h] - sm.ent_len[e]); }
+    if (lane == 0) {
+      sm.new_strsz = run;
+      // R5
+      sm.shstr_off = sm.cur;
+      sm.new_shoff = align_up(sm.cur + run, 8);
+      sm.total = sm.new_shoff + (uint64_t)(nk + 1) * 64;
+    }
   }
   __syncwarp();
   const uint32_t new_strsz = sm.new_strsz;

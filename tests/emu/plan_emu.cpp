@@ -49,6 +49,7 @@ static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline long long clock64() { return 0; }
 
 #define LB2_HOST_EMULATION 1
