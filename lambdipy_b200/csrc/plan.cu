@@ -306,6 +306,45 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
 
 // Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
 // Returns the new size; *err != 0 when objcopy would report corrupt notes.  Warp-collective.
+// Stable rank sort, one note per lane-iteration: position = #{j : cmp(j, i) < 0} + #{j < i : cmp(j, i) == 0}.
+// Equal to the merge sort above whenever the comparator is a consistent (strict weak) order.
+// Self-checking: if two notes claim the same position (only possible with an inconsistent comparator) the
+// permutation is left untouched and false is returned, so the caller can run the exact merge sort instead.
+__device__ bool warp_ranksort_notes(PlanSmem &sm, int n, bool second, int lane) {
+  const DNote *__restrict__ notes = sm.notes;
+  uint16_t *__restrict__ perm = sm.note_perm;
+  uint16_t *__restrict__ tmp = sm.note_tmp;
+  int bad = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    int r = 0;
+    if (i < n) {
+      const DNote me = notes[perm[i]];
+      for (int j = 0; j < n; j++) {
+        if (j == i) continue;
+        const DNote &o = notes[perm[j]];
+        const int c = second ? cmp_by_addr(sm, o, me) : cmp_by_attr(sm, o, me);
+        r += (c < 0) || (c == 0 && j < i);
+      }
+      tmp[r] = perm[i];
+    }
+    __syncwarp();
+    if (i < n && tmp[r] != perm[i]) bad = 1;   // someone else took this slot
+    __syncwarp();
+  }
+  // a slot claimed in one 32-note round can still be overwritten in a later one: re-check everything
+  for (int i = lane; i < n; i += 32) {
+    bool found = false;
+    const uint16_t mine = perm[i];
+    for (int j = 0; j < n && !found; j++) found = tmp[j] == mine;  // n <= 320
+    if (!found) bad = 1;
+  }
+  if (__ballot_sync(0xffffffffu, bad)) return false;
+  for (int i = lane; i < n; i += 32) perm[i] = tmp[i];
+  __syncwarp();
+  return true;
+}
+
 #ifdef LB2_PLAN_TIMING
 #define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
 #else
@@ -323,108 +362,139 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   long long nt_[8];
 #endif
   LB2_NT(0);
+  // 1. lane 0 walks the variable-length records (three words each) and records where every note starts
   if (lane == 0) {
     s_err = 0; s_skip = 0; s_n = 0;
     int n = 0;
     uint32_t remain = size, p = 0;
-    unsigned v1 = 0, v2 = 0, v3 = 0;
-    uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
     while (remain >= 12) {
       if (n >= note_cap) { s_err = 2; break; }
-      const uint8_t *h = nbuf + p;  // p stays a multiple of 4: aligned word loads
-      const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);
-      uint32_t namesz = hw[0], descsz = hw[1], type = hw[2];
-      uint32_t padded = (namesz + 3) & ~3u;
+      const uint32_t *hw = reinterpret_cast<const uint32_t *>(nbuf + p);  // p stays a multiple of 4
+      const uint32_t namesz = hw[0], descsz = hw[1];
+      const uint32_t padded = (namesz + 3) & ~3u;
       if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
-      if (type != 0x100 && type != 0x101) { s_err = 1; break; }
       if ((uint64_t)padded + descsz + 12 > remain) { s_err = 1; break; }
-      if (namesz < 3) { s_err = 1; break; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
-      const uint8_t *nm = h + 12, *desc = h + 12 + padded;
+      notes[n].off = (uint16_t)p;
+      perm[n] = (uint16_t)n;
       remain -= 12 + padded + descsz;
       p += 12 + padded + descsz;
-      DNote &d = notes[n];
-      d.off = (uint16_t)(h - nbuf);
-      d.namesz = (uint16_t)namesz;
-      d.type = type;
-      if (namesz > 2 && nm[0] == '$' && nm[1] == 1 && nm[2] == '1') v1++;
-      else if (namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) {
-        if (nm[4] == '2') v2++;
-        else if (nm[4] == '3') v3++;
-        else { s_err = 1; break; }
-      }
-      uint64_t start, end;
-      const uint32_t *dw = reinterpret_cast<const uint32_t *>(desc);
-      if (descsz == 0) start = end = 0;
-      else if (descsz == 4) { start = dw[0]; end = ~0ull; }
-      else if (descsz == 8) { start = dw[0]; end = dw[1]; }
-      else if (descsz == 16) { start = (uint64_t)dw[0] | ((uint64_t)dw[1] << 32); end = (uint64_t)dw[2] | ((uint64_t)dw[3] << 32); }
-      else { s_err = 1; break; }
-      if (start > end) start = end;
-      if (type == 0x100) {
-        if (start) pos = start;
-        d.start = pos;
-        if (end) poe = end;
-        d.end = poe;
-      } else {
-        if (start) pfs = start;
-        d.start = pfs;
-        if (end) pfe = end;
-        d.end = pfe;
-      }
-      if (nm[namesz - 1] != 0) { s_err = 1; break; }
-      perm[n] = (uint16_t)n;
       n++;
     }
     if (!s_err && remain != 0) s_err = 1;
-    if (!s_err) {
-      if (v1 == 0 && v2 == 0 && v3 == 0) v3 = 2;
-      if ((v1 && v2) || (v1 && v3) || (v2 && v3)) s_err = 1;
-      else if (v3 == 0) s_skip = 1;
-    }
     s_n = n;
   }
   __syncwarp();
   if (s_err) { *err = s_err; return size; }
-  if (s_skip || size < 12) {
-    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
-    return size;
-  }
   const int n = s_n;
+  // 2. every lane decodes its notes: checks, raw range, version class, comparison key and name hash
+  {
+    int bad = 0, v1 = 0, v2 = 0, v3 = 0;
+    for (int i = lane; i < n; i += 32) {
+      DNote &d = notes[i];
+      const uint8_t *h = nbuf + d.off;
+      const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);
+      const uint32_t namesz = hw[0], descsz = hw[1], type = hw[2];
+      const uint32_t padded = (namesz + 3) & ~3u;
+      if (type != 0x100 && type != 0x101) { bad = 1; continue; }
+      if (namesz < 3) { bad = 1; continue; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
+      const uint8_t *nm = h + 12;
+      const uint32_t *dw = reinterpret_cast<const uint32_t *>(h + 12 + padded);
+      d.namesz = (uint16_t)namesz;
+      d.type = type;
+      d.ver = 0;
+      if (nm[0] == '$' && nm[1] == 1 && nm[2] == '1') v1 = 1;
+      else if (namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) {
+        d.ver = 1;
+        if (nm[4] == '2') v2 = 1;
+        else if (nm[4] == '3') v3 = 1;
+        else { bad = 1; continue; }
+      }
+      uint64_t start, end;
+      if (descsz == 0) start = end = 0;
+      else if (descsz == 4) { start = dw[0]; end = ~0ull; }
+      else if (descsz == 8) { start = dw[0]; end = dw[1]; }
+      else if (descsz == 16) { start = (uint64_t)dw[0] | ((uint64_t)dw[1] << 32); end = (uint64_t)dw[2] | ((uint64_t)dw[3] << 32); }
+      else { bad = 1; continue; }
+      if (start > end) start = end;
+      d.start = start;   // raw; ranges inherited from earlier notes are filled in by step 3
+      d.end = end;
+      if (nm[namesz - 1] != 0) { bad = 1; continue; }
+      uint64_t key = 0;
+      uint32_t hsh = 2166136261u;
+      for (int q = 0; q < (int)namesz; q++) {
+        hsh = (hsh ^ nm[q]) * 16777619u;
+        if (q >= 3 && q < 11) key = (key << 8) | nm[q];
+      }
+      if (namesz <= 3) key = 0; else if (namesz < 11) key <<= 8 * (11 - namesz);
+      d.key = key;
+      d.pad = (uint8_t)hsh;             // low hash byte, cheap first filter
+      tmp[i] = (uint16_t)(hsh >> 8);
+    }
+    const unsigned mb = __ballot_sync(0xffffffffu, bad), m1 = __ballot_sync(0xffffffffu, v1), m2 = __ballot_sync(0xffffffffu, v2),
+                   m3 = __ballot_sync(0xffffffffu, v3);
+    if (mb) { *err = 1; return size; }
+    bool a1 = m1 != 0, a2 = m2 != 0, a3 = m3 != 0;
+    if (!a1 && !a2 && !a3) a3 = true;  // "version note missing - assuming version 3"
+    if ((a1 && a2) || (a1 && a3) || (a2 && a3)) { *err = 1; return size; }
+    if (!a3 || size < 12) {            // only v3 notes are merged
+      for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
+      return size;
+    }
+  }
   LB2_NT(1);
-  // per-note comparison aids, one note per lane-iteration
-  for (int i = lane; i < n; i += 32) {
-    DNote &d = notes[i];
-    const uint8_t *nm = nbuf + d.off + 12;
-    uint64_t key = 0;
-    uint32_t hsh = 2166136261u;
-    for (int q = 0; q < (int)d.namesz; q++) {
-      hsh = (hsh ^ nm[q]) * 16777619u;
-      if (q >= 3 && q < 11) key = (key << 8) | nm[q];
+  // 3. a note without a range inherits the previous OPEN / FUNC note's: inherently sequential, two words per note
+  if (lane == 0) {
+    uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
+    for (int i = 0; i < n; i++) {
+      DNote &d = notes[i];
+      const uint64_t start = d.start, end = d.end;
+      if (d.type == 0x100) {
+        if (start) pos = start;
+        if (end) poe = end;
+        d.start = pos; d.end = poe;
+      } else {
+        if (start) pfs = start;
+        if (end) pfe = end;
+        d.start = pfs; d.end = pfe;
+      }
     }
-    if (d.namesz <= 3) key = 0; else if (d.namesz < 11) key <<= 8 * (11 - d.namesz);
-    d.key = key;
-    d.ver = (d.namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) ? 1 : 0;
-    d.pad = (uint8_t)hsh;             // low hash byte, cheap first filter
-    tmp[i] = (uint16_t)(hsh >> 8);
   }
   __syncwarp();
-  for (int i = lane; i < n; i += 32) {
-    DNote &d = notes[i];
-    const uint8_t *nm = nbuf + d.off + 12;
-    int cls = i;
-    for (int j = 0; j < i; j++) {
-      const DNote &o = notes[j];
-      if (o.namesz != d.namesz || o.pad != d.pad || tmp[j] != tmp[i]) continue;
-      const uint8_t *om = nbuf + o.off + 12;
-      bool same = true;
-      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
-      if (same) { cls = j; break; }
+  // 4. equality classes of the names, and whether the first comparator is a consistent order on this input:
+  //    it is unless two notes whose names tie have nested ranges (a.start < b.start but a.end >= b.end) or two
+  //    different names tie on their common prefix; then (and only then) libc's merge sequence matters.
+  int exact_order;
+  {
+    int inconsistent = 0;
+    for (int i = lane; i < n; i += 32) {
+      DNote &d = notes[i];
+      const uint8_t *nm = nbuf + d.off + 12;
+      int cls = i;
+      for (int j = 0; j < i; j++) {
+        const DNote &o = notes[j];
+        if (o.namesz != d.namesz || o.pad != d.pad || tmp[j] != tmp[i]) continue;
+        const uint8_t *om = nbuf + o.off + 12;
+        bool same = true;
+        for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
+        if (same) { cls = j; break; }
+      }
+      d.cls = (uint16_t)cls;
     }
-    d.cls = (uint16_t)cls;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const DNote &d = notes[i];
+      for (int j = 0; j < n; j++) {
+        if (j == i) continue;
+        const DNote &o = notes[j];
+        if (o.cls != d.cls) { if (o.namesz != d.namesz && cmp_note_names(sm, o, d) == 0) inconsistent = 1; continue; }
+        if (o.start < d.start && o.end >= d.end) inconsistent = 1;
+      }
+    }
+    exact_order = __ballot_sync(0xffffffffu, inconsistent) != 0;
   }
-  __syncwarp();
   LB2_NT(2);
-  warp_msort_notes(sm, n, false, lane);
+  // consistent order: any stable sort gives the permutation libc's would; otherwise the restated merge sort
+  if (exact_order || !warp_ranksort_notes(sm, n, false, lane)) warp_msort_notes(sm, n, false, lane);
   LB2_NT(3);
   if (lane == 0) {
     for (int i = 0; i < n; i++) {
@@ -454,7 +524,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   }
   __syncwarp();
   LB2_NT(4);
-  warp_msort_notes(sm, n, true, lane);
+  if (!warp_ranksort_notes(sm, n, true, lane)) warp_msort_notes(sm, n, true, lane);  // (always consistent; msort never needed)
   LB2_NT(5);
   if (lane == 0) {
     // output offsets and range elision (depends on the previous surviving note): serial and cheap
@@ -1125,32 +1195,62 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   LB2_T(12);
   // ---- L. extents: every output byte is produced exactly once -- copied from the input arena,
   //         copied from the scratch slot, or zero-filled (BFD leaves gaps as file holes).
-  if (lane == 0) {
-    // content sections sorted by their new offset (insertion sort; inputs are nearly sorted)
+  {
+    // pieces = [headers] + content sections sorted by new offset + [.shstrtab] + [section table].  Rank sort
+    // across lanes (the keys are distinct unless sections overlap, which the gap check below rejects).
     int np = 0;
-    for (int k = 1; k < nk; k++) {
-      const int i = sm.order[k];
-      if (sm.sh[i].sh_type == SHT_NOBITS || sm.new_size[i] == 0) continue;
-      int q = np++;
-      while (q > 0 && sm.new_off[sm.piece[q - 1]] > sm.new_off[i]) { sm.piece[q] = sm.piece[q - 1]; q--; }
-      sm.piece[q] = (uint8_t)i;
+    for (int k0 = 0; k0 < nk; k0 += 32) {
+      const int k = k0 + lane;
+      bool content = false;
+      int i = 0;
+      if (k >= 1 && k < nk) { i = sm.order[k]; content = sm.sh[i].sh_type != SHT_NOBITS && sm.new_size[i] != 0; }
+      if (content) {
+        const uint64_t mine = sm.new_off[i];
+        int r = 0;
+        for (int q = 1; q < nk; q++) {
+          const int oi = sm.order[q];
+          if (q == k || sm.sh[oi].sh_type == SHT_NOBITS || sm.new_size[oi] == 0) continue;
+          const uint64_t o = sm.new_off[oi];
+          r += (o < mine) || (o == mine && q < k);
+        }
+        sm.piece[1 + r] = (uint8_t)i;
+      }
+      np += __popc(__ballot_sync(0xffffffffu, content));
     }
-    int ne = 0;
-    uint64_t pos = 0, copy_bytes = 0;
-    auto emit = [&](uint64_t src, uint64_t dst, uint64_t len) {
-      if (len == 0 || sm.fail) return;
-      if (dst < pos) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); return; }
-      if (dst > pos) { sm.ext_src[ne] = 0; sm.ext_dst[ne] = pos; sm.ext_len[ne] = dst - pos; ne++; }
-      sm.ext_src[ne] = src; sm.ext_dst[ne] = dst; sm.ext_len[ne] = len; ne++;
-      pos = dst + len;
-      copy_bytes += len;
+    __syncwarp();
+    const int total_pieces = np + 3;  // + headers, .shstrtab, section table
+    auto piece_of = [&](int q, uint64_t &src, uint64_t &dst, uint64_t &len) {
+      if (q == 0) { src = reinterpret_cast<uint64_t>(scr + SCR_EHDR); dst = 0; len = 64 + (uint64_t)new_phnum * 56; }
+      else if (q <= np) { const int i = sm.piece[q]; src = sm.src_addr[i]; dst = sm.new_off[i]; len = sm.new_size[i]; }
+      else if (q == np + 1) { src = reinterpret_cast<uint64_t>(scr + SCR_STR); dst = sm.shstr_off; len = new_strsz; }
+      else { src = reinterpret_cast<uint64_t>(scr + SCR_SHDR); dst = sm.new_shoff; len = (uint64_t)(nk + 1) * 64; }
     };
-    emit(reinterpret_cast<uint64_t>(scr + SCR_EHDR), 0, 64 + (uint64_t)new_phnum * 56);
-    for (int q = 0; q < np; q++) { const int i = sm.piece[q]; emit(sm.src_addr[i], sm.new_off[i], sm.new_size[i]); }
-    emit(reinterpret_cast<uint64_t>(scr + SCR_STR), sm.shstr_off, new_strsz);
-    emit(reinterpret_cast<uint64_t>(scr + SCR_SHDR), sm.new_shoff, (uint64_t)(nk + 1) * 64);
-    sm.n_ext = ne;
-    sm.cur = copy_bytes;
+    int ne = 0, bad = 0;
+    unsigned long long copy_bytes = 0;
+    for (int q0 = 0; q0 < total_pieces; q0 += 32) {
+      const int q = q0 + lane;
+      uint64_t src = 0, dst = 0, len = 0, prev_end = 0;
+      const bool valid = q < total_pieces;
+      if (valid) {
+        piece_of(q, src, dst, len);
+        if (q > 0) { uint64_t ps, pd, pl; piece_of(q - 1, ps, pd, pl); prev_end = pd + pl; }
+        if (dst < prev_end) bad = 1;   // overlapping output ranges: not a layout BFD would write
+      }
+      const bool gap = valid && dst > prev_end;
+      const unsigned gm = __ballot_sync(0xffffffffu, gap);
+      if (valid) {
+        int at = ne + lane + __popc(gm & ((1u << lane) - 1));
+        if (gap) { sm.ext_src[at] = 0; sm.ext_dst[at] = prev_end; sm.ext_len[at] = dst - prev_end; at++; }  // file hole
+        sm.ext_src[at] = src; sm.ext_dst[at] = dst; sm.ext_len[at] = len;
+        copy_bytes += len;
+      }
+      const int nvalid = total_pieces - q0 < 32 ? total_pieces - q0 : 32;
+      ne += nvalid + __popc(gm);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) copy_bytes += __shfl_xor_sync(0xffffffffu, copy_bytes, o);
+    if (__ballot_sync(0xffffffffu, bad)) { if (lane == 0) LB2_FAIL(ST_UNSUPPORTED_LAYOUT); }
+    if (lane == 0) { sm.n_ext = ne; sm.cur = copy_bytes; }
   }
   __syncwarp();
   if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }

@@ -42,6 +42,14 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
   g_bar->arrive_and_wait();
   return r;
 }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
+  uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
+  g_xchg[threadIdx.x] = raw;
+  g_bar->arrive_and_wait();
+  T r; memcpy(&r, &g_xchg[(threadIdx.x ^ m) & 31], sizeof r);
+  g_bar->arrive_and_wait();
+  return r;
+}
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
