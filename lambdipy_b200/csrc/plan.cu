@@ -29,6 +29,7 @@ struct DNote {
 template <int NB, int NN> struct NoteSmem {
   DNote notes[NN];
   uint16_t perm[NN], tmp[NN];
+  uint32_t tag[NN];
   __align__(16) uint8_t buf[NB];
 };
 constexpr int32_t ST_RETRY_BIG_NOTES = 100;  // internal: small-variant verdict, never leaves the device
@@ -68,6 +69,7 @@ struct PlanSmem {
   uint16_t *note_perm;
   uint16_t *note_tmp;
   uint8_t *note_buf;
+  uint32_t *note_tag;
   int note_cap_bytes, note_cap_n;
   // scalars shared by the warp
   int fail;
@@ -135,27 +137,65 @@ __device__ bool name_is(const char *n, const char *base) {  // "base" or "base.*
   return n[l] == 0 || n[l] == '.';
 }
 __device__ int expected_type_by_name(const char *n) {  // bfd/elf.c special_sections_*; -1: not a special name
-  if (name_is(n, ".bss") || name_is(n, ".tbss") || name_is(n, ".sbss") || name_is(n, ".lbss") || d_prefix(n, ".gnu.linkonce.b") || name_is(n, ".noinit")) return SHT_NOBITS;
-  if (d_streq(n, ".comment") || name_is(n, ".data") || name_is(n, ".data1") || d_prefix(n, ".debug") || d_streq(n, ".fini") || d_streq(n, ".got") ||
-      d_streq(n, ".init") || d_streq(n, ".interp") || d_prefix(n, ".line") || d_streq(n, ".plt") || name_is(n, ".rodata") || name_is(n, ".rodata1") ||
-      name_is(n, ".tdata") || name_is(n, ".text") || name_is(n, ".sdata") || name_is(n, ".ldata") || name_is(n, ".lrodata") || name_is(n, ".persistent") ||
-      d_prefix(n, ".gnu.linkonce.wi."))
-    return SHT_PROGBITS;
-  if (d_streq(n, ".dynamic")) return SHT_DYNAMIC;
-  if (d_streq(n, ".dynstr") || d_streq(n, ".strtab") || d_streq(n, ".shstrtab")) return SHT_STRTAB;
-  if (d_streq(n, ".dynsym")) return SHT_DYNSYM;
-  if (d_streq(n, ".symtab")) return SHT_SYMTAB;
-  if (name_is(n, ".fini_array")) return SHT_FINI_ARRAY;
-  if (name_is(n, ".init_array")) return SHT_INIT_ARRAY;
-  if (name_is(n, ".preinit_array")) return SHT_PREINIT_ARRAY;
-  if (d_streq(n, ".gnu.version")) return (int)SHT_GNU_VERSYM;
-  if (d_streq(n, ".gnu.version_d")) return (int)SHT_GNU_VERDEF;
-  if (d_streq(n, ".gnu.version_r")) return (int)SHT_GNU_VERNEED;
-  if (d_streq(n, ".gnu.hash")) return (int)SHT_GNU_HASH;
-  if (d_streq(n, ".hash")) return SHT_HASH;
-  if (d_prefix(n, ".note")) return SHT_NOTE;
-  if (d_prefix(n, ".rela")) return SHT_RELA;
-  if (name_is(n, ".rel")) return SHT_REL;
+  if (n[0] != '.') return -1;
+  switch (n[1]) {  // one group of literals per second character keeps this to a handful of compares
+    case 'b': if (name_is(n, ".bss")) return SHT_NOBITS; break;
+    case 'c': if (d_streq(n, ".comment")) return SHT_PROGBITS; break;
+    case 'd':
+      if (name_is(n, ".data") || name_is(n, ".data1") || d_prefix(n, ".debug")) return SHT_PROGBITS;
+      if (d_streq(n, ".dynamic")) return SHT_DYNAMIC;
+      if (d_streq(n, ".dynstr")) return SHT_STRTAB;
+      if (d_streq(n, ".dynsym")) return SHT_DYNSYM;
+      break;
+    case 'f':
+      if (d_streq(n, ".fini")) return SHT_PROGBITS;
+      if (name_is(n, ".fini_array")) return SHT_FINI_ARRAY;
+      break;
+    case 'g':
+      if (d_streq(n, ".got")) return SHT_PROGBITS;
+      if (n[2] == 'n' && n[3] == 'u' && n[4] == '.') {
+        if (d_streq(n, ".gnu.version")) return (int)SHT_GNU_VERSYM;
+        if (d_streq(n, ".gnu.version_d")) return (int)SHT_GNU_VERDEF;
+        if (d_streq(n, ".gnu.version_r")) return (int)SHT_GNU_VERNEED;
+        if (d_streq(n, ".gnu.hash")) return (int)SHT_GNU_HASH;
+        if (d_prefix(n, ".gnu.linkonce.b")) return SHT_NOBITS;
+        if (d_prefix(n, ".gnu.linkonce.wi.")) return SHT_PROGBITS;
+      }
+      break;
+    case 'h': if (d_streq(n, ".hash")) return SHT_HASH; break;
+    case 'i':
+      if (d_streq(n, ".init") || d_streq(n, ".interp")) return SHT_PROGBITS;
+      if (name_is(n, ".init_array")) return SHT_INIT_ARRAY;
+      break;
+    case 'l':
+      if (d_prefix(n, ".line") || name_is(n, ".ldata") || name_is(n, ".lrodata")) return SHT_PROGBITS;
+      if (name_is(n, ".lbss")) return SHT_NOBITS;
+      break;
+    case 'n':
+      if (d_prefix(n, ".note")) return SHT_NOTE;
+      if (name_is(n, ".noinit")) return SHT_NOBITS;
+      break;
+    case 'p':
+      if (d_streq(n, ".plt") || name_is(n, ".persistent")) return SHT_PROGBITS;
+      if (name_is(n, ".preinit_array")) return SHT_PREINIT_ARRAY;
+      break;
+    case 'r':
+      if (name_is(n, ".rodata") || name_is(n, ".rodata1")) return SHT_PROGBITS;
+      if (d_prefix(n, ".rela")) return SHT_RELA;
+      if (name_is(n, ".rel")) return SHT_REL;
+      break;
+    case 's':
+      if (name_is(n, ".sbss")) return SHT_NOBITS;
+      if (name_is(n, ".sdata")) return SHT_PROGBITS;
+      if (d_streq(n, ".strtab") || d_streq(n, ".shstrtab")) return SHT_STRTAB;
+      if (d_streq(n, ".symtab")) return SHT_SYMTAB;
+      break;
+    case 't':
+      if (name_is(n, ".tbss")) return SHT_NOBITS;
+      if (name_is(n, ".tdata") || name_is(n, ".text")) return SHT_PROGBITS;
+      break;
+    default: break;
+  }
   return -1;
 }
 __device__ bool type_is_known(uint32_t t) {
@@ -306,57 +346,19 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
 
 // Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
 // Returns the new size; *err != 0 when objcopy would report corrupt notes.  Warp-collective.
-// Stable rank sort, one note per lane-iteration: position = #{j : cmp(j, i) < 0} + #{j < i : cmp(j, i) == 0}.
-// Equal to the merge sort above whenever the comparator is a consistent (strict weak) order.
-// Self-checking: if two notes claim the same position (only possible with an inconsistent comparator) the
-// permutation is left untouched and false is returned, so the caller can run the exact merge sort instead.
-__device__ bool warp_ranksort_notes(PlanSmem &sm, int n, bool second, int lane) {
-  const DNote *__restrict__ notes = sm.notes;
-  uint16_t *__restrict__ perm = sm.note_perm;
-  uint16_t *__restrict__ tmp = sm.note_tmp;
-  int bad = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    int r = 0;
-    if (i < n) {
-      const DNote me = notes[perm[i]];
-      for (int j = 0; j < n; j++) {
-        if (j == i) continue;
-        const DNote &o = notes[perm[j]];
-        const int c = second ? cmp_by_addr(sm, o, me) : cmp_by_attr(sm, o, me);
-        r += (c < 0) || (c == 0 && j < i);
-      }
-      tmp[r] = perm[i];
-    }
-    __syncwarp();
-    if (i < n && tmp[r] != perm[i]) bad = 1;   // someone else took this slot
-    __syncwarp();
-  }
-  // a slot claimed in one 32-note round can still be overwritten in a later one: re-check everything
-  for (int i = lane; i < n; i += 32) {
-    bool found = false;
-    const uint16_t mine = perm[i];
-    for (int j = 0; j < n && !found; j++) found = tmp[j] == mine;  // n <= 320
-    if (!found) bad = 1;
-  }
-  if (__ballot_sync(0xffffffffu, bad)) return false;
-  for (int i = lane; i < n; i += 32) perm[i] = tmp[i];
-  __syncwarp();
-  return true;
-}
-
 #ifdef LB2_PLAN_TIMING
 #define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
 #else
 #define LB2_NT(k) do { } while (0)
 #endif
 __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out, int *err, int lane) {
-  __shared__ int s_n, s_err, s_skip;
+  __shared__ int s_n, s_err;
   __shared__ uint32_t s_newsize;
   DNote *__restrict__ notes = sm.notes;          // hoisted out of shared memory once
   uint16_t *__restrict__ perm = sm.note_perm;
   uint16_t *__restrict__ tmp = sm.note_tmp;
   const uint8_t *__restrict__ nbuf = sm.note_buf;
+  uint32_t *__restrict__ ntag = sm.note_tag;
   const int note_cap = sm.note_cap_n;
 #ifdef LB2_PLAN_TIMING
   long long nt_[8];
@@ -364,7 +366,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   LB2_NT(0);
   // 1. lane 0 walks the variable-length records (three words each) and records where every note starts
   if (lane == 0) {
-    s_err = 0; s_skip = 0; s_n = 0;
+    s_err = 0; s_n = 0;
     int n = 0;
     uint32_t remain = size, p = 0;
     while (remain >= 12) {
@@ -427,8 +429,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       }
       if (namesz <= 3) key = 0; else if (namesz < 11) key <<= 8 * (11 - namesz);
       d.key = key;
-      d.pad = (uint8_t)hsh;             // low hash byte, cheap first filter
-      tmp[i] = (uint16_t)(hsh >> 8);
+      ntag[i] = (hsh << 10) ^ namesz;  // name hash and length packed: one compare filters class candidates
     }
     const unsigned mb = __ballot_sync(0xffffffffu, bad), m1 = __ballot_sync(0xffffffffu, v1), m2 = __ballot_sync(0xffffffffu, v2),
                    m3 = __ballot_sync(0xffffffffu, v3);
@@ -460,41 +461,24 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     }
   }
   __syncwarp();
-  // 4. equality classes of the names, and whether the first comparator is a consistent order on this input:
-  //    it is unless two notes whose names tie have nested ranges (a.start < b.start but a.end >= b.end) or two
-  //    different names tie on their common prefix; then (and only then) libc's merge sequence matters.
-  int exact_order;
-  {
-    int inconsistent = 0;
-    for (int i = lane; i < n; i += 32) {
-      DNote &d = notes[i];
-      const uint8_t *nm = nbuf + d.off + 12;
-      int cls = i;
-      for (int j = 0; j < i; j++) {
-        const DNote &o = notes[j];
-        if (o.namesz != d.namesz || o.pad != d.pad || tmp[j] != tmp[i]) continue;
-        const uint8_t *om = nbuf + o.off + 12;
-        bool same = true;
-        for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
-        if (same) { cls = j; break; }
-      }
-      d.cls = (uint16_t)cls;
+  // 4. equality classes of the names (first note with identical name), one packed tag compare per candidate
+  for (int i = lane; i < n; i += 32) {
+    DNote &d = notes[i];
+    const uint8_t *nm = nbuf + d.off + 12;
+    const uint32_t tag = ntag[i];
+    int cls = i;
+    for (int j = 0; j < i; j++) {
+      if (ntag[j] != tag) continue;
+      const uint8_t *om = nbuf + notes[j].off + 12;
+      bool same = true;
+      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
+      if (same) { cls = j; break; }
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const DNote &d = notes[i];
-      for (int j = 0; j < n; j++) {
-        if (j == i) continue;
-        const DNote &o = notes[j];
-        if (o.cls != d.cls) { if (o.namesz != d.namesz && cmp_note_names(sm, o, d) == 0) inconsistent = 1; continue; }
-        if (o.start < d.start && o.end >= d.end) inconsistent = 1;
-      }
-    }
-    exact_order = __ballot_sync(0xffffffffu, inconsistent) != 0;
+    d.cls = (uint16_t)cls;
   }
+  __syncwarp();
   LB2_NT(2);
-  // consistent order: any stable sort gives the permutation libc's would; otherwise the restated merge sort
-  if (exact_order || !warp_ranksort_notes(sm, n, false, lane)) warp_msort_notes(sm, n, false, lane);
+  warp_msort_notes(sm, n, false, lane);   // restated glibc merge sort, level by level across lanes
   LB2_NT(3);
   if (lane == 0) {
     for (int i = 0; i < n; i++) {
@@ -524,7 +508,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   }
   __syncwarp();
   LB2_NT(4);
-  if (!warp_ranksort_notes(sm, n, true, lane)) warp_msort_notes(sm, n, true, lane);  // (always consistent; msort never needed)
+  warp_msort_notes(sm, n, true, lane);
   LB2_NT(5);
   if (lane == 0) {
     // output offsets and range elision (depends on the previous surviving note): serial and cheap
@@ -589,7 +573,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
 #endif
   LB2_T(0);
   if (lane == 0) {
-    sm.notes = ns.notes; sm.note_perm = ns.perm; sm.note_tmp = ns.tmp; sm.note_buf = ns.buf;
+    sm.notes = ns.notes; sm.note_perm = ns.perm; sm.note_tmp = ns.tmp; sm.note_buf = ns.buf; sm.note_tag = ns.tag;
     sm.note_cap_bytes = NB; sm.note_cap_n = NN;
   }
   const uint64_t base = a.in_off[f];
