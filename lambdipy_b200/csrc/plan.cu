@@ -289,9 +289,7 @@ __device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
   if (a.start > b.start) return 1;
   if (a.end > b.end) return -1;                        // larger ranges first
   if (a.end < b.end) return 1;
-  if (a.ver && !b.ver) return -1;
-  if (!a.ver && b.ver) return 1;
-  return 0;
+  return 0;  // ties keep the order of the first sort (stable merge)
 }
 
 // objcopy sorts the notes with libc qsort(); its first comparator is not antisymmetric for nested
@@ -648,6 +646,8 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       if (h.sh_type == SHT_NULL || h.sh_type == SHT_GROUP) err_uns = 1;
       if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
       if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
+      if (h.sh_type == 19 /* SHT_RELR */ && h.sh_entsize != 8) err_uns = 1;
+      if (h.sh_type == SHT_REL && h.sh_entsize != 16) err_uns = 1;
       if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
       {  // ---- gate (see expected_type_by_name)
         const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;

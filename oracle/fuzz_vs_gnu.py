@@ -23,11 +23,39 @@ def shdrs(b):
 
 def mutate(rng, src, dst, tmp):
     """returns a description or None if the mutation could not be applied"""
-    kind = rng.choice(["align", "entsize", "flags", "objcopy_add", "objcopy_remove", "objcopy_rename", "phdr", "link_info", "type", "addr", "multi"])
+    kind = rng.choice(["align", "entsize", "flags", "objcopy_add", "objcopy_remove", "objcopy_rename", "phdr", "link_info", "type", "addr", "multi",
+                       "notes_content", "notes_content"])
     shutil.copy(src, dst)
     with open(dst, "rb") as f:
         b = bytearray(f.read())
     shoff, shnum, shstr = shdrs(b)
+    if kind == "notes_content":
+        # corrupt / perturb the bytes of a build-attribute note section (sizes, types, ranges, names)
+        so, ss = struct.unpack_from("<QQ", b, shoff + shstr * 64 + 24)
+        names = bytes(b[so:so + ss])
+        cand = []
+        for k in range(1, shnum):
+            n, t = struct.unpack_from("<II", b, shoff + k * 64)
+            nm = names[n:names.index(b"\0", n)]
+            off, sz = struct.unpack_from("<QQ", b, shoff + k * 64 + 24)
+            if nm.startswith(b".gnu.build.attributes") and t == 7 and sz >= 12:
+                cand.append((off, sz))
+        if not cand:
+            return None
+        off, sz = rng.choice(cand)
+        for _ in range(rng.choice([1, 1, 2, 4])):
+            w = off + 4 * rng.randrange(sz // 4)
+            how = rng.random()
+            if how < 0.4:
+                struct.pack_into("<I", b, w, rng.choice([0, 1, 2, 3, 4, 7, 8, 12, 16, 20, 0x100, 0x101, 0x102, 0xffffffff]))
+            elif how < 0.7:
+                b[w + rng.randrange(4)] ^= 1 << rng.randrange(8)
+            else:
+                v, = struct.unpack_from("<I", b, w)
+                struct.pack_into("<I", b, w, (v + rng.choice([-16, -1, 1, 5, 16, 0x1000])) & 0xffffffff)
+        with open(dst, "wb") as f:
+            f.write(b)
+        return "notes_content @%#x+%d" % (off, sz)
     phnum, = struct.unpack_from("<H", b, 0x38)
     if shnum < 3:
         return None
@@ -120,6 +148,10 @@ def main():
     variants = F.build_variants(os.path.join(base, "fx"))
     seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
     seeds += [p for p in F.real_corpus("small") if os.path.getsize(p) < 2_000_000][:25]
+    for k, notes in F.note_scenarios().items():
+        p = os.path.join(base, "fx", k + ".so")
+        if F.with_build_notes(variants["c_plain"], p, notes):
+            seeds += [p, p]
     counts = {}
 
     def one(k):

@@ -183,8 +183,8 @@ static int cmp_notes_by_addr(const void *a, const void *b) {
   if (p1->start > p2->start) return 1;
   if (p1->end > p2->end) return -1;
   if (p1->end < p2->end) return 1;
-  if (note_is_version(p1) && !note_is_version(p2)) return -1;
-  if (!note_is_version(p1) && note_is_version(p2)) return 1;
+  /* ties keep the order of the first sort (the merge sort is stable) -- probe: a corrupted "HA$<version>"
+   * note stays between two version notes of the same range */
   return 0;
 }
 
@@ -212,7 +212,7 @@ static void msort_notes(BNote *b, size_t n, BNote *tmp, int (*cmp)(const void *,
 static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out, int *err) {
   *err = 0;
   memcpy(out, in, size);
-  if (size < 12) return size;
+  if (size == 0) return size;   /* objcopy skips empty note sections; 1..11 bytes are "excess data" -> corrupt */
   BNote *notes = (BNote *)calloc(size / 12 + 1, sizeof(BNote));
   BNote *pn = notes;
   uint64_t remain = size;
@@ -488,6 +488,8 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
     /* BFD refuses ("file format not recognized") symbol/reloc/versym tables with a foreign entsize */
     if ((h->sh_type == SHT_DYNSYM || h->sh_type == SHT_SYMTAB || h->sh_type == SHT_RELA) && h->sh_entsize != 24) UNSUP();
     if (h->sh_type == 0x6fffffff && h->sh_entsize != 2) UNSUP();
+    if (h->sh_type == 19 && h->sh_entsize != 8) UNSUP();   /* SHT_RELR */
+    if (h->sh_type == SHT_REL && h->sh_entsize != 16) UNSUP();
     if (!alloc && (h->sh_type == SHT_REL || h->sh_type == SHT_RELA)) UNSUP();
     /* ---- gate (see above) */
     {

@@ -173,3 +173,20 @@ def test_structure_fuzz_against_gnu_strip(oracle, variants, tmp_path):
         else:
             n_unsup += 1
     assert n_ok > 50 and n_unsup > 5
+
+
+def test_corrupt_and_tiny_note_sections_are_refused(oracle, variants, fixture_dir, tmp_path):
+    """objcopy reports 'corrupt GNU build attribute notes' and strip fails: the oracle (and the device
+    planner, tests/test_planner_emulated.py) must classify these as bad notes, not pass them through"""
+    import subprocess
+    for sz in (4, 8, 11, 12, 16, 20):
+        p = os.path.join(fixture_dir, "tiny_notes_%d.so" % sz)
+        sec = p + ".sec"
+        with open(sec, "wb") as f:
+            f.write(b"\x08\0\0\0" * (sz // 4) + b"\0" * (sz % 4))
+        subprocess.run(["objcopy", "--add-section", ".gnu.build.attributes=" + sec, "--set-section-flags",
+                        ".gnu.build.attributes=readonly", variants["c_plain"], p], check=True)
+        F.patch_section(p, ".gnu.build.attributes", sh_type=7)
+        data, gnu, rc, out, err = _diff(oracle, p, str(tmp_path))
+        assert gnu is None and "corrupt GNU build attribute" in err, (sz, err)
+        assert rc == 7, (sz, rc)

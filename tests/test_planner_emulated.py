@@ -94,3 +94,18 @@ def test_synthetic_corpus(emu, oracle):
     c = Corpus(40, seed=17, max_size=1 << 20)
     for i in range(len(c)):
         assert _agree(emu, oracle, c.materialize(i)) == 0
+
+
+def test_corrupt_note_sections(emu, oracle, variants, fixture_dir):
+    import subprocess
+    for sz in (4, 8, 11, 12, 20):
+        p = os.path.join(fixture_dir, "emu_tiny_notes_%d.so" % sz)
+        sec = p + ".sec"
+        with open(sec, "wb") as f:
+            f.write(b"\x08\0\0\0" * (sz // 4) + b"\0" * (sz % 4))
+        subprocess.run(["objcopy", "--add-section", ".gnu.build.attributes=" + sec, "--set-section-flags",
+                        ".gnu.build.attributes=readonly", variants["c_plain"], p], check=True)
+        F.patch_section(p, ".gnu.build.attributes", sh_type=7)
+        st, out = emu.strip(_read(p))
+        rc, _ = oracle.strip(_read(p))
+        assert st == 7 and rc == 7, (sz, st, rc)
