@@ -371,9 +371,9 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
       if (n >= note_cap) { s_err = 2; break; }
       const uint32_t *hw = reinterpret_cast<const uint32_t *>(nbuf + p);  // p stays a multiple of 4
       const uint32_t namesz = hw[0], descsz = hw[1];
-      const uint32_t padded = (namesz + 3) & ~3u;
+      const uint64_t padded = ((uint64_t)namesz + 3) & ~3ull;   // 64-bit: namesz = 0xffffffff must not wrap to 0
       if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
-      if ((uint64_t)padded + descsz + 12 > remain) { s_err = 1; break; }
+      if (padded + descsz + 12 > remain) { s_err = 1; break; }
       notes[n].off = (uint16_t)p;
       perm[n] = (uint16_t)n;
       remain -= 12 + padded + descsz;
@@ -1084,6 +1084,10 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   }
   __syncwarp();
   const uint32_t new_strsz = sm.new_strsz;
+  // sanity bound on the stripped size: re-layout can add LOAD alignment padding (at most a few MB per segment),
+  // never more; a larger value means wrapped address arithmetic on a hostile or corrupt file.  Also keeps the
+  // per-file tile count far inside 32 bits.
+  if (sm.total > n + (65ull << 20)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
   if (new_strsz > MAX_STR + 16) { if (lane == 0) { a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
   // blob: zero, then every non-merged name at its offset
   for (uint32_t i = lane; i < ((new_strsz + 15u) & ~15u); i += 32) scr[SCR_STR + i] = 0;
@@ -1219,6 +1223,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
         piece_of(q, src, dst, len);
         if (q > 0) { uint64_t ps, pd, pl; piece_of(q - 1, ps, pd, pl); prev_end = pd + pl; }
         if (dst < prev_end) bad = 1;   // overlapping output ranges: not a layout BFD would write
+        if (q == total_pieces - 1 && dst + len != sm.total) bad = 1;  // the section table must end the file
       }
       const bool gap = valid && dst > prev_end;
       const unsigned gm = __ballot_sync(0xffffffffu, gap);

@@ -21,9 +21,12 @@ def shdrs(b):
     return shoff, shnum, shstr
 
 
+ONLY_KINDS = None
+
+
 def mutate(rng, src, dst, tmp):
     """returns a description or None if the mutation could not be applied"""
-    kind = rng.choice(["align", "entsize", "flags", "objcopy_add", "objcopy_remove", "objcopy_rename", "phdr", "link_info", "type", "addr", "multi",
+    kind = rng.choice(ONLY_KINDS or ["align", "entsize", "flags", "objcopy_add", "objcopy_remove", "objcopy_rename", "phdr", "link_info", "type", "addr", "multi",
                        "notes_content", "notes_content"])
     shutil.copy(src, dst)
     with open(dst, "rb") as f:
@@ -142,7 +145,11 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--kinds", default=None, help="comma-separated subset of mutation kinds")
     a = ap.parse_args()
+    global ONLY_KINDS
+    if a.kinds:
+        ONLY_KINDS = a.kinds.split(",")
     oracle = oracle_lib.load()
     base = tempfile.mkdtemp(prefix="lb2fuzz_", dir="/dev/shm")
     variants = F.build_variants(os.path.join(base, "fx"))

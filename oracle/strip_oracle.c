@@ -225,6 +225,7 @@ static uint64_t merge_build_notes(const uint8_t *in, uint64_t size, uint8_t *out
     memcpy(&pn->descsz, p + 4, 4);
     memcpy(&pn->type, p + 8, 4);
     pn->padded_namesz = (pn->namesz + 3) & ~3u;
+    if (pn->namesz > 0xfffffff0u) goto bad;   /* objcopy computes in unsigned long: "note too big" */
     if (((pn->descsz + 3) & ~3u) != pn->descsz) goto bad;
     if (pn->type != NT_OPEN && pn->type != NT_FUNC) goto bad;
     if ((uint64_t)pn->padded_namesz + pn->descsz + 12 > remain) goto bad;
@@ -760,6 +761,7 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
   uint64_t new_shoff = align_up(cur, 8);
   uint64_t total = new_shoff + (uint64_t)new_shnum * 64;
 
+  if (total > n + ((uint64_t)65 << 20)) UNSUP();   /* wrapped address arithmetic on a corrupt file (see plan.cu) */
   out = (uint8_t *)calloc(total ? total : 1, 1);
   if (!out) { rc = LBO_NOMEM; goto done; }
 
