@@ -593,6 +593,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   else if (eh.e_ident[4] != 2 || eh.e_ident[5] != 1) st = ST_NOT_ELF64LE;
   else if (eh.e_type != 2 && eh.e_type != 3) st = ST_BAD_TYPE;
   else if (eh.e_machine != 62 && eh.e_machine != 183) st = ST_UNSUPPORTED_LAYOUT;
+  else if (eh.e_version != 1 || eh.e_ident[6] != 1 || eh.e_ehsize != 64) st = ST_UNSUPPORTED_LAYOUT;  // gate: BFD writes these itself
   else if (eh.e_shoff == 0 || eh.e_shnum == 0) st = ST_NO_SECTIONS;
   else if (eh.e_shentsize != 64 || (eh.e_phnum && eh.e_phentsize != 56)) st = ST_MALFORMED;
   else if (eh.e_shstrndx == 0xffff || eh.e_shnum >= 0xff00 || eh.e_phnum == 0xffff) st = ST_XINDEX;
@@ -628,7 +629,24 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   // ---- C. R1 keep/drop mask, lane i <-> sections i and i+32; verdicts combined by ballot
   {
     int err_mal = 0, err_uns = 0;
-    if (lane < phnum && sm.ph[lane].p_paddr != sm.ph[lane].p_vaddr) err_uns = 1;  // gate: section LMAs come from p_paddr
+    if (lane < phnum) {  // gate on the program headers (one per lane)
+      const Phdr &p = sm.ph[lane];
+      if (p.p_paddr != p.p_vaddr) err_uns = 1;                                   // section LMAs come from p_paddr
+      if (p.p_align & (p.p_align - 1)) err_uns = 1;                              // BFD: "invalid alignment"
+      if (p.p_type == PT_LOAD) {
+        if (p.p_align > 1 && ((p.p_vaddr - p.p_offset) & (p.p_align - 1))) err_uns = 1;
+        if (p.p_filesz > p.p_memsz || p.p_vaddr + p.p_memsz < p.p_vaddr || p.p_offset + p.p_filesz < p.p_offset) err_uns = 1;
+        for (int l = 0; l < lane; l++) {                                          // ascending, non-overlapping LOADs
+          const Phdr &o = sm.ph[l];
+          if (o.p_type != PT_LOAD) continue;
+          if (p.p_vaddr < o.p_vaddr + o.p_memsz) err_uns = 1;
+          if (p.p_filesz && o.p_filesz && p.p_offset < o.p_offset + o.p_filesz) err_uns = 1;
+        }
+      }
+      if (p.p_type == PT_PHDR && (p.p_offset != 64 || p.p_filesz != (uint64_t)phnum * 56 || p.p_memsz != (uint64_t)phnum * 56)) err_uns = 1;
+      if (p.p_type == PT_GNU_STACK && (p.p_offset || p.p_vaddr || p.p_filesz || p.p_memsz)) err_uns = 1;
+    }
+    if (lane < 8 && reinterpret_cast<const uint64_t *>(&sm.sh[0])[lane] != 0) err_uns = 1;  // section 0: the all-zero NULL header
     for (int i = lane; i < shnum; i += 32) {
       Shdr &h = sm.sh[i];
       sm.keep[i] = 0; sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
@@ -793,6 +811,8 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       for (int j = 0; j < phnum; j++)
         if (sm.ph[j].p_type == PT_LOAD && sec_in_seg(sm.sh[i], sm.ph[j])) { sg = j; break; }
       if (sg < 0) err = 1;
+      // gate: file offset and address of a loaded section move together (BFD: "lma adjusted" otherwise)
+      else if (sm.sh[i].sh_type != SHT_NOBITS && sm.sh[i].sh_offset - sm.ph[sg].p_offset != sm.sh[i].sh_addr - sm.ph[sg].p_vaddr) err = 1;
       sm.seg[i] = (int8_t)sg;
     }
     if (__ballot_sync(0xffffffffu, err)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
@@ -1153,6 +1173,7 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
         h.sh_info = 0;
         if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
       }
+      if (h.sh_flags & (0x10 | 0x20)) h.sh_entsize &= 0xffffffffu;  // SHF_MERGE/STRINGS: BFD carries entsize in an unsigned int
       switch (h.sh_type) {  // elf_fake_sections(): entsize of the types BFD knows
         case SHT_INIT_ARRAY: case SHT_FINI_ARRAY: case SHT_PREINIT_ARRAY: case 19 /* RELR */: h.sh_entsize = 8; break;
         case SHT_HASH: h.sh_entsize = 4; break;

@@ -441,6 +441,8 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
   memcpy(&eh, in, 64);
   if (eh.e_type != ET_DYN && eh.e_type != ET_EXEC) return LBO_BAD_TYPE;
   if (eh.e_machine != 62 && eh.e_machine != 183) return LBO_UNSUPPORTED_LAYOUT; /* x86-64, aarch64 only */
+  /* gate: BFD writes EV_CURRENT / sizeof(Ehdr) itself; a file that says otherwise is not linker output */
+  if (eh.e_version != 1 || in[6] != 1 || eh.e_ehsize != 64) return LBO_UNSUPPORTED_LAYOUT;
   if (eh.e_shoff == 0 || eh.e_shnum == 0) return LBO_NO_SECTIONS;
   if (eh.e_shentsize != 64 || (eh.e_phnum && eh.e_phentsize != 56)) return LBO_MALFORMED;
   if (eh.e_shstrndx == 0xffff || eh.e_shnum >= 0xff00 || eh.e_phnum == 0xffff) return LBO_XINDEX;
@@ -474,8 +476,32 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
         (S[i].h.sh_offset > n || S[i].h.sh_size > n - S[i].h.sh_offset)) { rc = LBO_MALFORMED; goto done; }
   }
 
-  for (uint64_t j = 0; j < phnum; j++)   /* gate: section LMAs come from p_paddr; Linux objects have paddr == vaddr */
+  for (uint64_t j = 0; j < phnum; j++) { /* gate: section LMAs come from p_paddr; Linux objects have paddr == vaddr */
     if (P[j].p_paddr != P[j].p_vaddr) UNSUP();
+    /* BFD refuses "a program header with invalid alignment"; loadable segments must be congruent */
+    if (P[j].p_align & (P[j].p_align - 1)) UNSUP();
+    if (P[j].p_type == PT_LOAD && P[j].p_align > 1 && ((P[j].p_vaddr - P[j].p_offset) & (P[j].p_align - 1))) UNSUP();
+    if (P[j].p_type == PT_PHDR && (P[j].p_offset != 64 || P[j].p_filesz != phnum * 56 || P[j].p_memsz != phnum * 56)) UNSUP();
+    if (P[j].p_type == PT_GNU_STACK && (P[j].p_offset || P[j].p_vaddr || P[j].p_filesz || P[j].p_memsz)) UNSUP();
+  }
+  {
+    /* gate: loadable segments are ascending and do not overlap, in memory or in the file */
+    uint64_t vend = 0, fend = 0;
+    int seen = 0;
+    for (uint64_t j = 0; j < phnum; j++) {
+      if (P[j].p_type != PT_LOAD) continue;
+      if (P[j].p_filesz > P[j].p_memsz) UNSUP();
+      if (P[j].p_vaddr + P[j].p_memsz < P[j].p_vaddr || P[j].p_offset + P[j].p_filesz < P[j].p_offset) UNSUP();
+      if (seen && (P[j].p_vaddr < vend || (P[j].p_filesz && P[j].p_offset < fend))) UNSUP();
+      vend = P[j].p_vaddr + P[j].p_memsz;
+      if (P[j].p_filesz) fend = P[j].p_offset + P[j].p_filesz;
+      seen = 1;
+    }
+  }
+  {
+    static const uint8_t zero64[64] = {0};
+    if (memcmp(in + eh.e_shoff, zero64, 64) != 0) UNSUP();   /* section 0 must be the all-zero NULL header */
+  }
 
   /* R1 */
   for (uint64_t i = 1; i < shnum; i++) {
@@ -585,6 +611,8 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
     for (uint64_t j = 0; j < phnum; j++)
       if (P[j].p_type == PT_LOAD && sec_in_seg(&S[i].h, &P[j])) { S[i].seg = (int)j; break; }
     if (S[i].seg < 0) UNSUP();
+    /* gate: file offset and address of a loaded section must move together ("lma adjusted" otherwise) */
+    if (S[i].h.sh_type != SHT_NOBITS && S[i].h.sh_offset - P[S[i].seg].p_offset != S[i].h.sh_addr - P[S[i].seg].p_vaddr) UNSUP();
   }
   for (uint64_t j = 0; j < phnum; j++) {
     pkeep[j] = 1;
@@ -825,6 +853,7 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
       h.sh_info = 0;
       if (target >= 0) { h.sh_info = (uint32_t)target; h.sh_flags |= SHF_INFO_LINK; }
     }
+    if (h.sh_flags & (0x10 | 0x20)) h.sh_entsize &= 0xffffffffu;   /* SHF_MERGE/STRINGS: BFD carries entsize in an unsigned int */
     /* elf.c elf_fake_sections(): BFD recomputes sh_entsize for the section types it knows
      * (probe: doctored sh_entsize on each section of a gcc-built .so, binutils 2.42). */
     switch (h.sh_type) {
