@@ -4,21 +4,33 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo (CUDA kernels)
   python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference's CPU pipeline
 
-Metric (BASELINE.json): ELF-strip GB/s of build-tree `.so` INPUT bytes.  One "step" = one pass of
-the hot path over one batch: every file of this rank's shard of the synthetic corpus (config 4 of
-BASELINE.json: sizes log-uniform 1 KB..128 MB, seed 0xB200, debug fraction U(0.05,0.8); 1250 files
-per GPU, i.e. the 10 000-file / ~100 GB corpus at 8 GPUs -- weak scaling, files are dealt size-sorted
-round-robin, no payload crosses GPUs; one NCCL allgather of per-rank byte counts per step).
+Metric (BASELINE.json): ELF-strip GB/s of build-tree `.so` INPUT bytes.
 
-  value     : device-resident.  Inputs already in HBM; timed = upload of offsets + plan kernel +
-              offset scan + compaction kernel + fetch of sizes/status (+ allgather when N > 1).
-  e2e       : the same batch through the C ABI with HOST buffers (lb2_strip_host): pinned H2D of
-              every input byte, kernels, D2H of every output byte, inside the timed region.
-  roofline  : compaction kernel, algorithmic bytes (copied extents read + output written) over its
-              CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+Workload (default, `--scaling strong`) = BASELINE config 4 as stated: the synthetic corpus of 10 000 `.so`
+files, sizes log-uniform 1 KB..128 MB (seed 0xB200, dropped fraction U(0.05,0.8); 115 GB in, 67 GB out),
+dealt size-sorted round-robin over the N ranks -- the SAME 10 000 files at every N (at N=8 this is also
+config 5, "100 GB over 8 B200").  One "step" = one pass of the hot path over the rank's whole shard.  A
+shard whose input + output does not fit in HBM side by side (N=1: 115 + 67 GB) keeps the input resident
+and streams the output through a two-slot ring (lb2_strip_device_chunked), one batch per ~14 GB chunk.
+`--scaling weak` is round 1's workload (1250 files per GPU).  No payload crosses GPUs; the one collective
+is a single NCCL allgather of the per-rank byte counts after the last step, inside the timed region.
+
+  value      device-resident: inputs already in HBM; timed = upload of offsets + plan kernel + offset scan +
+             compaction kernel + fetch of sizes/status per batch, + the allgather.  CUDA events, max over ranks.
+  e2e        the same hot path through the C ABI with HOST buffers (lb2_strip_host on pinned arenas placed on
+             the GPU's NUMA node): headers and kept extents cross PCIe up, stripped files come down, inside the
+             timed region.  Host memory bounds it to the first <= 15 GB of each rank's shard.
+  tree       (N=1) lb2_strip_tree -- the call that replaces project_build.py:260 -- on a /dev/shm tree holding
+             the same files the reference arm strips: file reads and in-place writes included.
+  roofline   compaction kernel: algorithmic bytes (copied extents read + output written) over its CUDA-event
+             duration against MEASURED_PEAKS.json hbm_gbs; every rank's figure is in `per_rank`.
   cpu_baseline / --impl reference: the reference's own line `find DIR/ -name "*.so" | xargs strip`
-              (/root/reference/lambdipy/project_build.py:260) on /dev/shm over a size-balanced 1/8
-              sample of the same corpus: serial as the reference runs it, and `xargs -P nproc -n 1`.
+             (/root/reference/lambdipy/project_build.py:260) on /dev/shm over the first <= 15 GB of the
+             corpus (1/8: ~1250 files): serial as the reference runs it, and `xargs -P nproc -n 1`.
+  parity     after the timed region every rank strips 8 size-stratified files of ITS shard with the real
+             `strip --strip-unneeded` and compares them byte for byte with what the GPU produced.
+  real_trees (N=1) BASELINE configs 2 and 3 (stand-ins from this image's site-packages): kernels, tree call,
+             reference line, fallback count.
 """
 import argparse
 import ctypes as C
@@ -30,13 +42,17 @@ import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "ELF-strip GB/s (build-tree .so bytes)"
+TOTAL_FILES = 10000
 FILES_PER_GPU = 1250
 SEED = 0xB200
+SAMPLE_SPAN = 15 << 30        # host-side legs (e2e, tree, CPU baseline) work on the first <= 15 GiB of a shard
+LAUNCHES_PER_BATCH = 4        # plan (small + large note workspace), scan, compaction
 
 
 def peaks():
@@ -142,47 +158,64 @@ REF_LINE = 'find {d}/ -name "*.so" | xargs strip'              # project_build.p
 PAR_LINE = 'find {d}/ -name "*.so" | xargs -P {p} -n 1 strip'  # same tool, all host cores
 
 
-def _materialize(args):
-    corpus, i, path = args
-    with open(path, "wb") as f:
-        f.write(corpus.materialize(i))
-    return os.path.getsize(path)
+def shm_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") else None
 
 
-def cpu_strip_bench(write_master, n_bytes, steps, warmup, parallel_only=False):
-    """write_master(dir) populates dir with *.so inputs.  Returns GB/s of the reference line, serial
-    and with -P nproc.  Each timed run works on a fresh copy (strip rewrites files in place)."""
+def copy_tree_parallel(src, dst, threads=32):
+    """cp -r with many threads (the trees are tens of GB of tmpfs; strip rewrites files in place, so every
+    timed run needs a fresh copy).  Keeps symlinks and modes."""
+    jobs = []
+    for d, dirs, fs in os.walk(src):
+        rel = os.path.relpath(d, src)
+        os.makedirs(os.path.join(dst, rel), exist_ok=True)
+        for f in fs:
+            jobs.append((os.path.join(d, f), os.path.join(dst, rel, f)))
+        for x in list(dirs):
+            if os.path.islink(os.path.join(d, x)):
+                jobs.append((os.path.join(d, x), os.path.join(dst, rel, x)))
+
+    def cp(j):
+        s, t = j
+        if os.path.islink(s):
+            os.symlink(os.readlink(s), t)
+        else:
+            shutil.copyfile(s, t)
+            shutil.copymode(s, t)
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(cp, jobs))
+
+
+def run_line(line, d, nproc):
+    t0 = time.perf_counter()
+    rc = subprocess.run(["bash", "-c", "set -e; set -o pipefail; " + line.format(d=d, p=nproc)], capture_output=True)
+    dt = time.perf_counter() - t0
+    if rc.returncode != 0:
+        raise RuntimeError("reference strip pipeline failed: %s" % rc.stderr.decode()[:300])
+    return dt
+
+
+def cpu_lines_on_master(base, master, n_bytes, par_reps, par_warm, serial_reps):
+    """Times the reference's line on fresh copies of `master`.  Returns the result dict and leaves the
+    last parallel run's stripped tree in base/run_ref for comparisons."""
     nproc = os.cpu_count() or 1
-    base = tempfile.mkdtemp(prefix="lb2_cpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    try:
-        master = os.path.join(base, "master")
-        os.makedirs(master)
-        write_master(master)
-
-        def timed(line, reps, warm):
-            best, times = None, []
-            for r in range(warm + reps):
-                run = os.path.join(base, "run")
-                shutil.copytree(master, run)
-                cmd = line.format(d=run, p=nproc)
-                t0 = time.perf_counter()
-                rc = subprocess.run(["bash", "-c", "set -e; set -o pipefail; " + cmd], capture_output=True)
-                dt = time.perf_counter() - t0
-                shutil.rmtree(run)
-                if rc.returncode != 0:
-                    raise RuntimeError("reference strip pipeline failed: %s" % rc.stderr.decode()[:300])
-                if r >= warm:
-                    times.append(dt)
-            return times
-
-        par = timed(PAR_LINE, steps, warmup)
-        ser = [] if parallel_only else timed(REF_LINE, max(1, min(steps, 2)), 0)
-        res = {"bytes": n_bytes, "nproc": nproc,
-               "parallel_s": par, "parallel_gbs": n_bytes / 1e9 / (sum(par) / len(par)),
-               "serial_s": ser, "serial_gbs": (n_bytes / 1e9 / (sum(ser) / len(ser))) if ser else None}
-        return res
-    finally:
-        shutil.rmtree(base, ignore_errors=True)
+    par, ser = [], []
+    run = os.path.join(base, "run_ref")
+    for r in range(par_warm + par_reps):
+        shutil.rmtree(run, ignore_errors=True)
+        copy_tree_parallel(master, run)
+        dt = run_line(PAR_LINE, run, nproc)
+        if r >= par_warm:
+            par.append(dt)
+    run2 = os.path.join(base, "run_ser")
+    for r in range(serial_reps):
+        shutil.rmtree(run2, ignore_errors=True)
+        copy_tree_parallel(master, run2)
+        ser.append(run_line(REF_LINE, run2, nproc))
+    shutil.rmtree(run2, ignore_errors=True)
+    return {"bytes": n_bytes, "nproc": nproc, "parallel_s": par, "parallel_gbs": n_bytes / 1e9 / (sum(par) / len(par)),
+            "serial_s": ser, "serial_gbs": (n_bytes / 1e9 / (sum(ser) / len(ser))) if ser else None}
 
 
 def strip_version():
@@ -192,33 +225,123 @@ def strip_version():
         return "unknown"
 
 
-# ---------------------------------------------------------------- arms
+def gnu_strip(data, workdir, tag):
+    """`strip --strip-unneeded -o OUT IN` of the real binary (the parity oracle of last resort)."""
+    pi, po = os.path.join(workdir, "p%s.in.so" % tag), os.path.join(workdir, "p%s.out.so" % tag)
+    with open(pi, "wb") as f:
+        f.write(data)
+    r = subprocess.run(["strip", "--strip-unneeded", "-o", po, pi], capture_output=True)
+    out = None
+    if r.returncode == 0:
+        with open(po, "rb") as f:
+            out = f.read()
+    for p in (pi, po):
+        if os.path.exists(p):
+            os.unlink(p)
+    return out
+
+
+def trees_identical(a, b, threads=32):
+    la, lb = [], []
+    for root, acc in ((a, la), (b, lb)):
+        for d, _, fs in os.walk(root):
+            for f in fs:
+                acc.append(os.path.relpath(os.path.join(d, f), root))
+    if sorted(la) != sorted(lb):
+        return False
+
+    def same(rel):
+        pa, pb = os.path.join(a, rel), os.path.join(b, rel)
+        if os.path.islink(pa) or os.path.islink(pb):
+            return os.path.islink(pa) and os.path.islink(pb) and os.readlink(pa) == os.readlink(pb)
+        if os.path.getsize(pa) != os.path.getsize(pb):
+            return False
+        with open(pa, "rb") as fa, open(pb, "rb") as fb:
+            while True:
+                x, y = fa.read(1 << 24), fb.read(1 << 24)
+                if x != y:
+                    return False
+                if not x:
+                    return True
+
+    with ThreadPoolExecutor(threads) as ex:
+        return all(ex.map(same, la))
+
+
+# ---------------------------------------------------------------- workload
+def make_corpus(a, rank, world):
+    from lambdipy_b200.corpus import Corpus
+    if a.scaling == "strong":
+        return Corpus(a.total_files, seed=SEED, rank=rank, world=world)
+    return Corpus(a.files_per_gpu * world, seed=SEED, rank=rank, world=world)
+
+
+def sample_count(corpus):
+    """Number of leading files of the shard whose arena span is <= SAMPLE_SPAN."""
+    import numpy as np
+    return int(np.searchsorted(corpus.off[1:], SAMPLE_SPAN, side="right"))
+
+
+def workload_config(a, world):
+    if a.scaling == "strong":
+        w = ("synthetic ELF corpus, BASELINE config 4 at full size (= config 5 at 8 GPUs): %d files, sizes log-uniform 1 KB-128 MB, "
+             "seed 0x%X, dropped fraction U(0.05,0.8), ~115 GB in / ~67 GB out; the same files at every N, dealt size-sorted "
+             "round-robin over %d rank(s)" % (a.total_files, SEED, world))
+    else:
+        w = ("synthetic ELF corpus (BASELINE config 4/5 generator): %d files per GPU (%d total), sizes log-uniform 1 KB-128 MB, "
+             "seed 0x%X, dropped fraction U(0.05,0.8); files dealt size-sorted round-robin over ranks" %
+             (a.files_per_gpu, a.files_per_gpu * world, SEED))
+    return {"workload": w, "total_files": a.total_files if a.scaling == "strong" else a.files_per_gpu * world,
+            "parallelism": "file-sharded x%d, no payload exchange, one allgather of byte counts" % world,
+            "l2": "inputs (>10 GB per GPU) far larger than the 126 MB L2; no flush needed"}
+
+
+def _materialize(args):
+    corpus, i, path = args
+    with open(path, "wb") as f:
+        f.write(corpus.materialize(i))
+    return os.path.getsize(path)
+
+
+# ---------------------------------------------------------------- reference arm
 def run_reference(a, rank, world):
     if rank != 0:
         return 0
-    from lambdipy_b200.corpus import Corpus
     from multiprocessing import Pool
-    # the same 1/8 size-balanced sample of the N=1 workload that the b200 arm's cpu_baseline uses
-    sample = Corpus(a.files_per_gpu, seed=SEED, rank=0, world=8)
-    n_bytes = sample.total_bytes
-
-    def write_master(d):
-        jobs = [(sample, i, os.path.join(d, "f%05d.so" % i)) for i in range(len(sample))]
-        with Pool(min(32, os.cpu_count() or 1)) as pool:
-            pool.map(_materialize, jobs, chunksize=4)
-
-    res = cpu_strip_bench(write_master, n_bytes, a.steps, max(a.warmup, 1))
+    corpus = make_corpus(a, 0, 1)          # the host-side legs always use the head of the whole corpus
+    ns = sample_count(corpus)
+    n_bytes = int(corpus.sizes[:ns].sum())
+    base = tempfile.mkdtemp(prefix="lb2_ref_", dir=shm_dir())
+    try:
+        master = os.path.join(base, "master")
+        os.makedirs(master)
+        jobs = [(corpus, i, os.path.join(master, "f%05d.so" % i)) for i in range(ns)]
+        with Pool(min(48, os.cpu_count() or 1)) as pool:
+            pool.map(_materialize, jobs, chunksize=2)
+        # bound the run: K timed + W warm-up parallel runs must end within a few minutes; the serial line once
+        t_probe0 = time.perf_counter()
+        res = cpu_lines_on_master(base, master, n_bytes, 1, 0, 1)
+        per_run = (time.perf_counter() - t_probe0) / 2
+        budget = 240.0
+        steps = max(1, min(a.steps, int(budget / max(per_run, 1e-3)) - 1))
+        warm = max(0, min(a.warmup, steps // 4))
+        more = cpu_lines_on_master(base, master, n_bytes, steps, warm, 0) if steps > 1 else None
+        if more:
+            res["parallel_s"] = more["parallel_s"]; res["parallel_gbs"] = more["parallel_gbs"]
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
     value = res["parallel_gbs"]
+    sample = ("the first %d files (%.3f GB, 1 KB-128 MB each) of the corpus on /dev/shm, every timed run on a fresh copy; `%s` "
+              "(GNU strip: %s) with all %d host cores; %d timed runs%s; serial as the reference runs it (1 process): %.3f GB/s"
+              % (ns, n_bytes / 1e9, PAR_LINE.format(d="DIR", p=res["nproc"]), strip_version(), res["nproc"], len(res["parallel_s"]),
+                 "" if len(res["parallel_s"]) == a.steps else " (of --steps %d: bounded to a few minutes)" % a.steps, res["serial_gbs"] or 0))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * sum(res["parallel_s"]) / len(res["parallel_s"]),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(a, world),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": res["nproc"], "kind": "reference",
-                         "sample": "size-balanced 1/8 of the N=1 workload: %d files, %.3f GB on /dev/shm; `%s` (GNU strip: %s); "
-                                   "serial as the reference runs it (1 process): %.3f GB/s" %
-                                   (len(sample), n_bytes / 1e9, PAR_LINE.format(d="DIR", p=res["nproc"]), strip_version(), res["serial_gbs"] or 0),
-                         "serial_value": res["serial_gbs"]},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": res["nproc"], "kind": "reference", "sample": sample,
+                         "serial_value": res["serial_gbs"], "timed_runs": len(res["parallel_s"])},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,20 +349,86 @@ def run_reference(a, rank, world):
     return 0
 
 
-def workload_config(a, world):
-    return {"workload": "synthetic ELF corpus (BASELINE config 4/5): %d files per GPU (%d total), sizes log-uniform 1 KB-128 MB, "
-                        "seed 0x%X, dropped fraction U(0.05,0.8); files dealt size-sorted round-robin over ranks" %
-                        (a.files_per_gpu, a.files_per_gpu * world, SEED),
-            "files_per_gpu": a.files_per_gpu, "parallelism": "file-sharded x%d, no payload exchange" % world,
-            "l2": "inputs (>10 GB per GPU) far larger than the 126 MB L2; no flush needed"}
+# ---------------------------------------------------------------- real build trees (BASELINE configs 2, 3)
+REAL_TREES = {
+    "config2_numpy+scipy+sklearn+PIL": ["numpy", "scipy", "sklearn", "PIL", "numpy.libs", "scipy.libs", "pillow.libs", "scikit_learn.libs"],
+    "config3_torch (stand-in for tensorflow 1.13.1)": ["torch"],
+}
 
 
+def real_trees_block(ctx, peak):
+    """Kernels, tree call and the reference's line on copies of this image's real wheels (N=1, rank 0)."""
+    import numpy as np
+    import sysconfig
+    from lambdipy_b200 import strip as S
+    from lambdipy_b200.device import DeviceBatch
+    sp = sysconfig.get_paths()["purelib"]
+    out = {}
+    nproc = os.cpu_count() or 1
+    for name, roots in REAL_TREES.items():
+        roots = [r for r in roots if os.path.isdir(os.path.join(sp, r))]
+        if not roots:
+            continue
+        base = tempfile.mkdtemp(prefix="lb2_real_", dir=shm_dir())
+        try:
+            master = os.path.join(base, "master")
+            for r in roots:
+                shutil.copytree(os.path.join(sp, r), os.path.join(master, r), symlinks=True,
+                                ignore=lambda d, names: [n for n in names if not (os.path.isdir(os.path.join(d, n)) or ".so" in n)])
+            files = sorted(os.path.join(d, f) for d, _, fs in os.walk(master) for f in fs
+                           if f.endswith(".so") and not os.path.islink(os.path.join(d, f)))
+            in_bytes = sum(os.path.getsize(p) for p in files)
+            ref = os.path.join(base, "ref")
+            ser, par = [], []
+            for _ in range(2):
+                shutil.rmtree(ref, ignore_errors=True); copy_tree_parallel(master, ref)
+                par.append(run_line(PAR_LINE, ref, nproc))
+            for _ in range(2):
+                shutil.rmtree(ref, ignore_errors=True); copy_tree_parallel(master, ref)
+                ser.append(run_line(REF_LINE, ref, nproc))
+            gpu = os.path.join(base, "gpu")
+            tt = []
+            for _ in range(3):
+                shutil.rmtree(gpu, ignore_errors=True); copy_tree_parallel(master, gpu)
+                t0 = time.perf_counter()
+                st = S.strip_tree(gpu, ctx=ctx)
+                tt.append(time.perf_counter() - t0)
+            same = trees_identical(ref, gpu)
+            blobs = [open(p, "rb").read() for p in files]
+            b = DeviceBatch.from_blobs(ctx, blobs)
+            plan, comp = [], []
+            for k in range(15):
+                b.strip_async(); d = b.results()
+                if k >= 5:
+                    plan.append(d["plan_ms"]); comp.append(d["compact_ms"])
+            b.close()
+            pm, cm = float(np.median(plan)), float(np.median(comp))
+            alg = d["copy_bytes"] + d["out_bytes"]
+            out[name] = {
+                "files": len(files), "in_gb": in_bytes / 1e9, "out_gb": d["out_bytes"] / 1e9, "fallback_files": int(st["n_fallback"]),
+                "unsupported_on_device": int(d["n_unsupported"]), "plan_ms": pm, "compact_ms": cm,
+                "compact_frac": alg / 1e9 / (cm / 1e3) / peak, "whole_pass_frac": (alg + d["header_bytes"]) / 1e9 / ((pm + cm) / 1e3) / peak,
+                "kernels_gbs_input": in_bytes / 1e9 / ((pm + cm) / 1e3),
+                "tree_s": min(tt), "tree_first_call_s": tt[0], "tree_gbs": in_bytes / 1e9 / min(tt),
+                "tree_phases_s": {k: st[k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s")},
+                "tree_identical_to_reference": bool(same),
+                "reference_serial_s": min(ser), "reference_serial_gbs": in_bytes / 1e9 / min(ser),
+                "reference_parallel_s": min(par), "reference_parallel_gbs": in_bytes / 1e9 / min(par), "cores": nproc,
+            }
+        finally:
+            shutil.rmtree(base, ignore_errors=True)
+    return out
+
+
+# ---------------------------------------------------------------- B200 arm
 def run_b200(a, rank, local_rank, world):
-    os.environ["NCCL_DEBUG"] = os.environ.get("LB2_NCCL_DEBUG", "NONE")  # NCCL prints its version banner on stdout at any level >= VERSION; bench prints ONE JSON line
+    # NCCL's INFO lines (communicator, nranks, transport) go to stderr; stdout carries the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG", os.environ.get("LB2_NCCL_DEBUG", "INFO"))
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
     from lambdipy_b200 import _native as N
-    from lambdipy_b200.corpus import Corpus
     from lambdipy_b200.device import DeviceBatch
 
     torch.cuda.set_device(local_rank)
@@ -248,18 +437,19 @@ def run_b200(a, rank, local_rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = N.Context(local_rank)
-    corpus = Corpus(a.files_per_gpu * world, seed=SEED, rank=rank, world=world)
-    batch = DeviceBatch.from_corpus(ctx, corpus)
+    peak, peak_src = peaks()
+    corpus = make_corpus(a, rank, world)
+    n = len(corpus)
+    in_span = int(corpus.off[-1])
+    free_b, total_b = torch.cuda.mem_get_info()
+    chunked = (2 * in_span + n * 4096 + (1 << 30)) > 0.85 * free_b
+    chunk_bytes = int(a.chunk_gb * (1 << 30)) if chunked else None
+    batch = DeviceBatch.from_corpus(ctx, corpus, chunk_bytes=chunk_bytes)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
+    counts_h = torch.zeros(4, dtype=torch.int64).pin_memory()
     counts = torch.zeros(4, dtype=torch.int64, device="cuda")
     gathered = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
-    # The allgather of the per-rank counters runs on a side stream: the next batch does not have to
-    # wait for the slowest rank's counters (files never move between GPUs); the timed region ends
-    # only after every step's allgather has completed.
-    side = torch.cuda.Stream() if world > 1 else None
-    ring = [(torch.zeros(4, dtype=torch.int64, device="cuda"), torch.zeros(4 * world, dtype=torch.int64, device="cuda")) for _ in range(8)] if world > 1 else []
-    ring_pos = [0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,19 +458,24 @@ def run_b200(a, rank, local_rank, world):
             torch.cuda.synchronize()
 
     def step():
+        if chunked:
+            return batch.strip_chunked(stream=sptr)
         batch.strip_async(stream=sptr)
-        st = batch.results()
-        if dist:  # the one collective of the path: per-rank byte counts (32 bytes per rank)
-            c, g = ring[ring_pos[0] % len(ring)]
-            ring_pos[0] += 1
-            with torch.cuda.stream(side):
-                c.copy_(torch.tensor([st["in_bytes"], st["out_bytes"], st["n_ok"], st["n_unsupported"]], dtype=torch.int64), non_blocking=True)
-                dist.all_gather_into_tensor(g, c)
-        return st
+        return batch.results()
 
-    for _ in range(max(a.warmup, 3)):
+    def allgather_counts(st):
+        # the ONE collective of the path: per-rank byte counts, 32 bytes per rank, pinned source
+        counts_h[0], counts_h[1], counts_h[2], counts_h[3] = st["in_bytes"], st["out_bytes"], st["n_ok"], st["n_unsupported"]
+        counts.copy_(counts_h, non_blocking=True)
+        dist.all_gather_into_tensor(gathered, counts)
+
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
         st = step()
-    assert st["n_unsupported"] == 0 and st["n_ok"] == len(corpus), st
+    if dist:
+        allgather_counts(st)  # communicator + NVLS buffers come up outside the timed region
+    assert st["n_unsupported"] == 0 and st["n_ok"] == n, st
+    n_batches = 1 if not chunked else int(np.ceil(in_span / batch.chunk_bytes))  # reported; exact count below
     # ---- device-resident timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -292,47 +487,63 @@ def run_b200(a, rank, local_rank, world):
     for _ in range(a.steps):
         st = step()
         compact_ms.append(st["compact_ms"]); plan_ms.append(st["plan_ms"])
-    if side is not None:
-        stream.wait_stream(side)  # every step's allgather is inside the timed region
+    if dist:
+        allgather_counts(st)
     e1.record(stream)
     barrier()
-    if dist:
-        g = ring[(ring_pos[0] - 1) % len(ring)][1].cpu().numpy().reshape(world, 4)
-        assert int(g[:, 2].sum()) == a.files_per_gpu * world and int(g[:, 3].sum()) == 0, g
     dev_ms = e0.elapsed_time(e1)
+    if dist:
+        g = gathered.cpu().numpy().reshape(world, 4)
+        total_files = a.total_files if a.scaling == "strong" else a.files_per_gpu * world
+        assert int(g[:, 2].sum()) == total_files and int(g[:, 3].sum()) == 0, g
+    cms, pms = sum(compact_ms) / len(compact_ms), sum(plan_ms) / len(plan_ms)
+    alg = st["copy_bytes"] + st["out_bytes"]
     if a.profile_mode:
-        from lambdipy_b200.sharding import gather_counts
-        per_rank = gather_counts([int(1e3 * sum(compact_ms) / len(compact_ms)), int(1e3 * sum(plan_ms) / len(plan_ms)),
-                                  st["copy_bytes"] + st["out_bytes"], int(1e3 * dev_ms / a.steps)], device="cuda")
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": dev_ms / a.steps, "compact_ms": compact_ms, "plan_ms": plan_ms,
-                              "per_rank_[compact_us, plan_us, alg_bytes, step_us]": per_rank.tolist(),
-                              "per_rank_compact_frac": [float(r[2]) / 1e9 / (r[0] / 1e6) / peaks()[0] for r in per_rank.tolist()],
-                              "note": "not a bench value"}))
+                              "alg_bytes": alg, "frac": alg / 1e9 / (cms / 1e3) / peak, "chunked": chunked, "note": "not a bench value"}))
         batch.close()
         if dist:
             dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- end to end through host buffers
-    in_span = int(corpus.off[-1])
-    h_in = ctx.pinned_alloc(in_span + 256)
-    out_cap = in_span + len(corpus) * 4096 + (16 << 20)
+    # ---- parity on the shard that was benchmarked: 8 size-stratified files per rank vs the real GNU strip
+    order = np.argsort(batch.sizes[:n], kind="stable")
+    picks = sorted(set(int(order[min(n - 1, (k * (n - 1)) // 7)]) for k in range(8)))
+    got = {}
+    if chunked:
+        def grab(chunk, f0, cnt, d_slot, ooff, osz, stat):
+            for i in picks:
+                if f0 <= i < f0 + cnt:
+                    buf = C.create_string_buffer(int(osz[i - f0]))
+                    ctx.d2h(buf, d_slot + int(ooff[i - f0]), len(buf))
+                    got[i] = buf.raw
+        batch.strip_chunked(stream=sptr, on_chunk=grab)
+    else:
+        for i in picks:
+            got[i] = batch.read_output(i)
+    pdir = tempfile.mkdtemp(prefix="lb2_par_%d_" % rank, dir=shm_dir())
+    mismatches = 0
+    for i in picks:
+        want = gnu_strip(batch.read_input(i), pdir, str(i))
+        mismatches += (want is None) or (want != got.get(i))
+    shutil.rmtree(pdir, ignore_errors=True)
+
+    # ---- end to end through host buffers (the first <= 15 GiB of the shard)
+    ns = sample_count(corpus) if in_span > SAMPLE_SPAN else n
+    s_span = int(corpus.off[ns])
+    h_in = ctx.pinned_alloc(s_span + 256)
+    out_cap = s_span + ns * 4096 + (16 << 20)
     h_out = ctx.pinned_alloc(out_cap)
-    batch.read_input_arena(h_in)
-    n = len(corpus)
-    out_off = np.zeros(n + 1, dtype=np.uint64); out_sizes = np.zeros(n, dtype=np.uint64); status = np.zeros(n, dtype=np.int32)
+    ctx.d2h(h_in, batch.d_in, s_span)
+    out_off = np.zeros(ns + 1, dtype=np.uint64); out_sizes = np.zeros(ns, dtype=np.uint64); status = np.zeros(ns, dtype=np.int32)
     u64p = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint64))
     hst = N.Stats()
 
     def e2e_step():
-        ctx.check(ctx.lib.lb2_strip_host(ctx.h, h_in, u64p(batch.off), u64p(batch.sizes), n, h_out, out_cap, u64p(out_off), u64p(out_sizes),
+        ctx.check(ctx.lib.lb2_strip_host(ctx.h, h_in, u64p(batch.off), u64p(batch.sizes), ns, h_out, out_cap, u64p(out_off), u64p(out_sizes),
                                          status.ctypes.data_as(C.POINTER(C.c_int32)), 0, C.byref(hst)))
-        if dist:
-            counts.copy_(torch.tensor([hst.in_bytes, hst.out_bytes, hst.n_ok, hst.n_unsupported], dtype=torch.int64), non_blocking=True)
-            dist.all_gather_into_tensor(gathered, counts)
-            torch.cuda.synchronize()
 
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
 
@@ -342,89 +553,101 @@ def run_b200(a, rank, local_rank, world):
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
+        if dist:
+            allgather_counts({"in_bytes": hst.in_bytes, "out_bytes": hst.out_bytes, "n_ok": hst.n_ok, "n_unsupported": hst.n_unsupported})
         barrier()
         return (time.perf_counter() - t0) * 1e3
 
     # default path of lb2_strip_host: zero-copy over the mapped pinned arenas; then, for comparison, the
     # staged pipeline (explicit H2D of whole files -> kernels in HBM -> D2H, 256 MB chunks on 3 streams)
     e2e_ms = time_e2e()
-    zc_stats = (hst.in_bytes, hst.out_bytes, hst.copy_bytes)
+    e2e_in, e2e_out, e2e_up = hst.in_bytes, hst.out_bytes, hst.copy_bytes + hst.header_bytes
+    assert hst.n_ok == ns and int(status.max()) == 0
+    probe = int(np.argsort(batch.sizes[:ns])[ns // 2])  # host result of one mid-sized file == what GNU strip / the device path gave
+    e2e_probe = C.string_at(h_out + int(out_off[probe]), int(out_sizes[probe]))
     os.environ["LB2_HOST_ZEROCOPY"] = "0"
     staged_ms = time_e2e()
     os.environ.pop("LB2_HOST_ZEROCOPY")
     clocks = sampler.stop() if rank == 0 else None  # sampled across the device-resident and the e2e timed regions
-    assert hst.n_ok == n and int(status.max()) == 0
-    # e2e result check: host output of one mid-sized file equals the device-resident result
-    probe = int(np.argsort(batch.sizes)[n // 2])
-    assert C.string_at(h_out + int(out_off[probe]), int(out_sizes[probe])) == batch.read_output(probe)
+    pdir = tempfile.mkdtemp(prefix="lb2_par_%d_" % rank, dir=shm_dir())
+    mismatches += gnu_strip(batch.read_input(probe), pdir, "e2e") != e2e_probe
+    shutil.rmtree(pdir, ignore_errors=True)
 
-    # ---- reduce over ranks: totals, max time
+    # ---- reduce over ranks: totals, max time, every rank's kernel figures
     local = torch.tensor([st["in_bytes"], st["out_bytes"], st["copy_bytes"], st["header_bytes"], st["n_ok"], st["n_unsupported"],
-                          float(in_span)], dtype=torch.float64, device="cuda")
-    times = torch.tensor([dev_ms, e2e_ms, sum(compact_ms) / len(compact_ms), sum(plan_ms) / len(plan_ms), staged_ms], dtype=torch.float64, device="cuda")
+                          float(e2e_in), float(e2e_out), float(e2e_up), float(s_span), float(len(picks) + 1), float(mismatches)],
+                         dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_ms, staged_ms], dtype=torch.float64, device="cuda")
+    mine = torch.tensor([cms, pms, dev_ms / a.steps, float(alg), float(st["in_bytes"]), e2e_ms / e2e_steps], dtype=torch.float64, device="cuda")
+    allr = torch.zeros(6 * world, dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(local, op=dist.ReduceOp.SUM)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    tot_in, tot_out, tot_copy, tot_hdr, n_ok, n_uns, tot_span = [float(x) for x in local.tolist()]
-    dev_ms, e2e_ms, cms, pms, staged_ms = [float(x) for x in times.tolist()]
+        dist.all_gather_into_tensor(allr, mine)
+    else:
+        allr.copy_(mine)
+    tot_in, tot_out, tot_copy, tot_hdr, n_ok, n_uns, te_in, te_out, te_up, te_span, n_par, n_bad = [float(x) for x in local.tolist()]
+    dev_ms, e2e_ms, staged_ms = [float(x) for x in times.tolist()]
+    per_rank = [{"rank": r, "compact_ms": v[0], "plan_ms": v[1], "step_ms": v[2], "frac": v[3] / 1e9 / (v[0] / 1e3) / peak,
+                 "in_gb": v[4] / 1e9, "e2e_ms": v[5]} for r, v in enumerate(allr.cpu().numpy().reshape(world, 6).tolist())]
 
     if rank == 0:
         ms_per_step = dev_ms / a.steps
         value = tot_in / 1e9 / (ms_per_step / 1e3)
-        e2e_value = tot_in / 1e9 / (e2e_ms / e2e_steps / 1e3)
-        peak, peak_src = peaks()
-        # dominant kernel: compaction.  Algorithmic bytes per launch on THIS rank = C + OUT.
-        alg = (st["copy_bytes"] + st["out_bytes"])
-        achieved = alg / 1e9 / (sum(compact_ms) / len(compact_ms) / 1e3)
-        traffic = None
+        e2e_value = te_in / 1e9 / (e2e_ms / e2e_steps / 1e3)
+        achieved = alg / 1e9 / (cms / 1e3)
+        batches_per_step = 1
+        if chunked:
+            b_, f_ = 0, 0
+            while f_ < n:
+                g_ = f_ + 1
+                while g_ < n and int(corpus.off[g_ + 1] - corpus.off[f_]) <= batch.chunk_bytes:
+                    g_ += 1
+                b_ += 1; f_ = g_
+            batches_per_step = b_
+        wkey = "%s:%d:%d:%x" % (a.scaling, a.total_files if a.scaling == "strong" else a.files_per_gpu, world, SEED)
+        traffic, tnote = None, "no ncu capture for this workload in profiles/traffic.json"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get("compact_dram_bytes_per_launch")
+                    tj = json.load(f)
+                if tj.get("workload_key") == wkey:  # a capture of another workload says nothing about this one
+                    traffic = tj.get("compact_dram_bytes_per_launch")
+                    tnote = tj.get("how")
             except Exception:
                 pass
-        cpu = None
-        if world == 1 and not a.no_cpu_baseline:
-            sample = Corpus(a.files_per_gpu, seed=SEED, rank=0, world=8)
-            full = {int(g): i for i, g in enumerate(corpus.global_index)}
-
-            def write_master(d):
-                for k, g in enumerate(sample.global_index):
-                    with open(os.path.join(d, "f%05d.so" % k), "wb") as f:
-                        f.write(batch.read_input(full[int(g)]))
-
-            nb = sum(int(batch.sizes[full[int(g)]]) for g in sample.global_index)
-            r = cpu_strip_bench(write_master, nb, 2, 1)
-            cpu = {"value": r["parallel_gbs"], "unit": "GB/s", "cores": r["nproc"], "kind": "reference",
-                   "sample": "size-balanced 1/8 of this workload (%d files, %.3f GB) on /dev/shm through the reference's line "
-                             "`find DIR/ -name \"*.so\" | xargs strip` with -P %d -n 1 (%s); serial (1 process, as the reference runs it): %.3f GB/s"
-                             % (len(sample), nb / 1e9, r["nproc"], strip_version(), r["serial_gbs"]),
-                   "serial_value": r["serial_gbs"]}
         line = {
-            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": workload_config(a, world),
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": dict(workload_config(a, world), batches_per_step_rank0=batches_per_step,
+                                                               output_ring="two slots of %.1f GB (input + output exceed HBM)" % (batch.slot_cap / 1e9) if chunked else None),
             "totals": {"files": int(n_ok), "unsupported_files": int(n_uns), "in_gb": tot_in / 1e9, "out_gb": tot_out / 1e9,
                        "copied_gb": tot_copy / 1e9, "header_gb": tot_hdr / 1e9},
             "roofline": {"bound": "hbm", "kernel": "lb2_compact_kernel" if os.environ.get("LB2_COMPACT_TMA") == "0" else "lb2_compact_tma_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg, "kernel_ms": sum(compact_ms) / len(compact_ms),
-                         "plan_kernel_ms": sum(plan_ms) / len(plan_ms),
-                         "whole_pass_frac": (alg + st["header_bytes"]) / 1e9 / ((sum(compact_ms) + sum(plan_ms)) / len(compact_ms) / 1e3) / peak},
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(tot_copy + tot_hdr),
-                    "d2h_bytes_per_step": int(tot_out), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "lb2_strip_host on pinned, device-mapped host arenas: kernels pull headers + kept extents over PCIe and "
-                           "push stripped files back (dropped sections never cross the bus)",
-                    "staged": {"value": tot_in / 1e9 / (staged_ms / e2e_steps / 1e3), "ms_per_step": staged_ms / e2e_steps,
-                               "h2d_bytes_per_step": int(tot_span), "d2h_bytes_per_step": int(tot_out),
+                         "traffic": traffic, "traffic_note": tnote, "traffic_workload_key": wkey, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg / batches_per_step, "kernel_ms": cms / batches_per_step,
+                         "launches_per_step": batches_per_step, "plan_kernel_ms": pms / batches_per_step,
+                         "whole_pass_frac": (alg + st["header_bytes"]) / 1e9 / ((cms + pms) / 1e3) / peak,
+                         "rank": 0, "min_frac_over_ranks": min(r["frac"] for r in per_rank)},
+            "per_rank": per_rank,
+            "parity": {"against": "strip --strip-unneeded -o OUT IN (%s), byte for byte" % strip_version(), "files_checked": int(n_par),
+                       "mismatches": int(n_bad), "what": "8 size-stratified outputs of every rank's own shard after the timed region + 1 output of the host-buffer path"},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(te_up), "d2h_bytes_per_step": int(te_out),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "in_bytes_per_step": int(te_in),
+                    "workload": "the first %d files (%.2f GB) of each rank's shard -- host memory bounds it" % (ns, s_span / 1e9) if ns < n else "every rank's whole shard",
+                    "api": "lb2_strip_host on pinned, device-mapped host arenas on the GPU's NUMA node: kernels pull headers + kept extents "
+                           "over PCIe and push stripped files back (dropped sections never cross the bus)",
+                    "staged": {"value": te_in / 1e9 / (staged_ms / e2e_steps / 1e3), "ms_per_step": staged_ms / e2e_steps,
+                               "h2d_bytes_per_step": int(te_span), "d2h_bytes_per_step": int(te_out),
                                "api": "LB2_HOST_ZEROCOPY=0: cudaMemcpyAsync of whole files in 256 MB chunks on 3 streams"}},
-            "gpu_launches": 4 * a.steps,  # plan (2 variants), scan, compaction per step
+            "gpu_launches": LAUNCHES_PER_BATCH * batches_per_step * a.steps,
             "clocks": clocks,
         }
-        if cpu:
-            line["cpu_baseline"] = cpu
+        assert n_bad == 0, "parity sample failed: %d mismatches" % n_bad
+        if world == 1 and not a.no_host_legs:
+            line.update(host_legs(a, ctx, corpus, batch, ns, peak))
         print(json.dumps(line))
     ctx.pinned_free(h_in); ctx.pinned_free(h_out)
     batch.close()
@@ -434,15 +657,75 @@ def run_b200(a, rank, local_rank, world):
     return 0
 
 
+def host_legs(a, ctx, corpus, batch, ns, peak):
+    """N=1 only: the reference's line and lb2_strip_tree on the SAME /dev/shm tree, and the real build trees."""
+    from lambdipy_b200 import strip as S
+    out = {}
+    n_bytes = int(corpus.sizes[:ns].sum())
+    base = tempfile.mkdtemp(prefix="lb2_cpu_", dir=shm_dir())
+    try:
+        free = shutil.disk_usage(base).free
+        if free < 3.2 * n_bytes:
+            out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": "skipped: /dev/shm has %.1f GB free, the sample tree needs %.1f GB" % (free / 1e9, 3.2 * n_bytes / 1e9)}
+            return out
+        master = os.path.join(base, "master")
+        os.makedirs(master)
+
+        def dump(i):
+            with open(os.path.join(master, "f%05d.so" % i), "wb") as f:
+                f.write(batch.read_input(i))
+
+        with ThreadPoolExecutor(8) as ex:  # cudaMemcpy D2H + tmpfs write per file
+            list(ex.map(dump, range(ns)))
+        r = cpu_lines_on_master(base, master, n_bytes, 2, 1, 1)
+        out["cpu_baseline"] = {
+            "value": r["parallel_gbs"], "unit": "GB/s", "cores": r["nproc"], "kind": "reference",
+            "sample": "the first %d files (%.3f GB) of the corpus as a /dev/shm tree, fresh copy per run, through the reference's line "
+                      "`find DIR/ -name \"*.so\" | xargs strip` with -P %d -n 1 (%s), mean of 2 runs after 1 warm-up; serial (1 process, "
+                      "as the reference runs it): %.3f GB/s" % (ns, n_bytes / 1e9, r["nproc"], strip_version(), r["serial_gbs"]),
+            "serial_value": r["serial_gbs"]}
+        # ---- the product call on the same tree: walk + read + H2D + kernels + D2H + in-place write
+        gpu = os.path.join(base, "run_gpu")
+        tt, sts = [], []
+        for _ in range(3):
+            shutil.rmtree(gpu, ignore_errors=True)
+            copy_tree_parallel(master, gpu)
+            t0 = time.perf_counter()
+            st = S.strip_tree(gpu, ctx=ctx)
+            tt.append(time.perf_counter() - t0); sts.append(st)
+        same = trees_identical(os.path.join(base, "run_ref"), gpu)
+        best = min(range(len(tt)), key=lambda k: tt[k])
+        out["tree"] = {"value": n_bytes / 1e9 / tt[best], "unit": "GB/s", "s": tt[best], "first_call_s": tt[0], "runs_s": tt,
+                       "files": ns, "in_gb": n_bytes / 1e9, "fallback_files": int(sts[best]["n_fallback"]), "failed_files": int(sts[best]["n_failed"]),
+                       "phases_s": {k: sts[best][k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s")},
+                       "identical_to_reference_tree": bool(same),
+                       "vs_reference_parallel": (n_bytes / 1e9 / tt[best]) / r["parallel_gbs"], "vs_reference_serial": (n_bytes / 1e9 / tt[best]) / r["serial_gbs"],
+                       "api": "lb2_strip_tree (the call that replaces project_build.py:260) on a fresh /dev/shm copy of the tree the reference line strips"}
+        assert same and sts[best]["n_failed"] == 0, "tree leg: GPU-stripped tree differs from the reference-stripped tree"
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+    if not a.no_real_trees:
+        try:
+            out["real_trees"] = real_trees_block(ctx, peak)
+        except Exception as e:  # the stand-in wheels are an image detail; the synthetic line must survive their absence
+            out["real_trees"] = {"error": repr(e)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--files-per-gpu", type=int, default=FILES_PER_GPU)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--total-files", type=int, default=TOTAL_FILES, help="strong scaling: files in the whole corpus")
+    ap.add_argument("--files-per-gpu", type=int, default=FILES_PER_GPU, help="weak scaling: files per GPU")
+    ap.add_argument("--chunk-gb", type=float, default=14.0, help="output-ring chunk when input + output exceed HBM")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-legs", action="store_true", help="skip cpu_baseline / tree / real_trees (N=1)")
+    ap.add_argument("--no-real-trees", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (for runs under ncu; not a bench value)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -11,8 +11,9 @@
  * binding placed at that spot calls instead (see INTEGRATION.md for the reference-side stub):
  *
  *   lb2_strip_tree()          == the whole shell line: select basename "*.so" under a root
- *                                (find, :260), strip each regular ELF in place (strip, :260),
- *                                preserving mode, replacing via temp file + rename.
+ *                                (find, :260), strip each regular ELF in place (strip, :260) the way
+ *                                GNU strip 2.42 does: new contents written into the EXISTING inode
+ *                                (mode, owner and other hard links kept; mtime not).
  *   lb2_strip_host()          == `strip` over a batch of files already read into host memory
  *                                (what xargs hands to one strip process), results to host memory.
  *   lb2_strip_device_async()  == the same batch with input and output arenas resident in HBM
@@ -70,6 +71,7 @@ enum {
 #define LB2_TREE_FALLBACK_HOST_STRIP 0x100u /* unsupported ELF files: run the host `strip` on them  */
 #define LB2_TREE_TOLERATE_NON_ELF    0x200u /* non-ELF "*.so": leave untouched (reference: rc 123)   */
 #define LB2_TREE_DRY_RUN             0x400u /* plan + compact, write nothing                         */
+#define LB2_TREE_CLEANUP             0x800u /* also do the script's rm lines (project_build.py:256-259) on the walk */
 
 typedef struct lb2_stats {
   uint32_t n_files, n_ok, n_unsupported, overflow;
@@ -90,9 +92,12 @@ typedef struct lb2_tree_stats {
   uint32_t n_fallback;        /* handed to the host `strip`                                     */
   uint32_t n_skipped;         /* symlinks, directories, tolerated non-ELF                       */
   uint32_t n_failed;          /* would make the reference's script exit non-zero                */
-  uint32_t pad;
+  uint32_t n_removed;         /* LB2_TREE_CLEANUP: *.egg-info, *.dist-info, __pycache__, tests entries removed */
   uint64_t in_bytes, out_bytes;
-  double walk_read_s, gpu_s, write_s, fallback_s;
+  double walk_read_s;         /* directory walk + stat                                          */
+  double gpu_s;               /* kernels + result fetch, summed over batches                    */
+  double write_s;             /* file reads/uploads and downloads/writes (overlapped), wall     */
+  double fallback_s;          /* host `strip` on the files the planner refused                  */
   lb2_stats batch;
 } lb2_tree_stats;
 
@@ -106,7 +111,7 @@ int lb2_sm_count(const lb2_ctx *ctx);
 /* ---- device / pinned memory for callers without their own CUDA runtime (ctypes) ---------- */
 void *lb2_dev_alloc(lb2_ctx *ctx, uint64_t bytes);
 void lb2_dev_free(lb2_ctx *ctx, void *p);
-void *lb2_pinned_alloc(lb2_ctx *ctx, uint64_t bytes);
+void *lb2_pinned_alloc(lb2_ctx *ctx, uint64_t bytes); /* pinned + device-mapped, on the GPU's NUMA node (LB2_NUMA=0: anywhere) */
 void lb2_pinned_free(lb2_ctx *ctx, void *p);
 int lb2_memcpy_h2d(lb2_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
 int lb2_memcpy_d2h(lb2_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
@@ -124,6 +129,23 @@ int lb2_strip_device_async(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_
 int lb2_batch_results(lb2_ctx *ctx, uint64_t *h_out_off /* n+1 */, uint64_t *h_out_sizes /* n */,
                       int32_t *h_status /* n */, lb2_stats *stats);
 
+/* ---- strip a shard whose input + output do not fit side by side in HBM ------------------------- */
+/* Input arena resident (as above); the output is streamed through a ring of TWO slots of slot_capacity
+ * bytes each at d_out_ring: consecutive files are grouped into chunks of <= max_chunk_bytes of arena span
+ * (0 = slot_capacity), chunk k is written to slot k % 2 and handed to on_chunk (may be NULL) before the
+ * slot is reused two chunks later -- the consumer owns the slot only for the duration of the callback.
+ * Offsets passed to the callback are relative to the slot.  h_out_sizes / h_status (n_files each, may be
+ * NULL) receive the per-file results; *total sums the chunks (plan_ms / compact_ms: summed kernel times).
+ * This is what one `strip` process does to an argument list longer than memory: SURVEY.md D7, the
+ * 10 000-file corpus of BASELINE config 4 on one GPU (/root/reference/lambdipy/project_build.py:260). */
+typedef int (*lb2_chunk_fn)(void *user, uint32_t chunk, uint32_t first_file, uint32_t n_files, const void *d_out_slot,
+                            const uint64_t *out_off, const uint64_t *out_sizes, const int32_t *status,
+                            const lb2_stats *chunk_stats);
+int lb2_strip_device_chunked(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                             uint32_t n_files, void *d_out_ring, uint64_t slot_capacity, uint64_t max_chunk_bytes,
+                             uint32_t flags, void *stream, lb2_chunk_fn on_chunk, void *user, uint64_t *h_out_sizes,
+                             int32_t *h_status, lb2_stats *total);
+
 /* ---- strip a batch held in host memory ---------------------------------------------------- */
 /* h_out_off[f] (multiples of 256) and h_out_sizes[f] describe where file f was written in h_out.
  * When both arenas are pinned and device-mapped (lb2_pinned_alloc, cudaHostAlloc, cudaHostRegister) the
@@ -137,6 +159,22 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in, const uint64_t *h_in_off, con
 /* ---- strip a directory tree in place (the reference's shell line) ------------------------ */
 int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix /* ".so" */, uint32_t flags,
                    lb2_tree_stats *stats);
+/* The same with the sibling clean-up lines of the reference's script folded into the directory walk
+ * (flag LB2_TREE_CLEANUP; /root/reference/lambdipy/project_build.py:256-259):
+ *     rm -rf ROOT/{glob}.egg-info ROOT/{glob}.dist-info          (top level only, shell glob: no dot files)
+ *     find ROOT/ -name __pycache__ | xargs rm -rf
+ *     find ROOT/ -name tests | grep -v "KEEP" | xargs rm -rf      KEEP = keep_tests_regex, a grep basic regex on
+ *                                                                the printed path; the reference passes "*" when
+ *                                                                --keep-tests is not given, 'a\|b' otherwise (:249)
+ * They run before the selection, as in the script: objects under a removed directory are not stripped. */
+int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t flags, const char *keep_tests_regex,
+                      lb2_tree_stats *stats);
+/* Only the clean-up lines (no GPU, no context needed). */
+int lb2_tree_cleanup(const char *root, const char *keep_tests_regex, uint32_t *n_removed);
+/* Optional: pay lb2_strip_tree's first-use costs (pinned slot ring, I/O streams, device workspaces) now,
+ * e.g. on a helper thread while the reference's script is still running pip
+ * (/root/reference/lambdipy/project_build.py:266-268).  expected_tree_bytes sizes the ring (0 = default). */
+int lb2_tree_prepare(lb2_ctx *ctx, uint64_t expected_tree_bytes);
 
 /* ---- plan only: per-file output sizes and status, nothing copied (tests) ------------------ */
 int lb2_plan_device(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,

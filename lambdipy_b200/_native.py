@@ -15,7 +15,7 @@ LB2_OK, LB2_E_CUDA, LB2_E_ARG, LB2_E_CAPACITY, LB2_E_IO, LB2_E_NODEVICE, LB2_E_S
 ST_OK, ST_NOT_ELF, ST_NOT_ELF64LE, ST_BAD_TYPE, ST_NO_SECTIONS, ST_XINDEX = 0, 1, 2, 3, 4, 5
 ST_UNSUPPORTED_LAYOUT, ST_BAD_NOTES, ST_PLANNER_LIMIT, ST_MALFORMED = 6, 7, 8, -1
 F_NO_MERGE_NOTES = 1
-TREE_FALLBACK_HOST_STRIP, TREE_TOLERATE_NON_ELF, TREE_DRY_RUN = 0x100, 0x200, 0x400
+TREE_FALLBACK_HOST_STRIP, TREE_TOLERATE_NON_ELF, TREE_DRY_RUN, TREE_CLEANUP = 0x100, 0x200, 0x400, 0x800
 
 EXPORTS = [
     "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_version", "lb2_sm_count",
@@ -23,6 +23,7 @@ EXPORTS = [
     "lb2_memcpy_h2d", "lb2_memcpy_d2h", "lb2_memset_d",
     "lb2_strip_device_async", "lb2_batch_results", "lb2_strip_host", "lb2_strip_tree",
     "lb2_plan_device", "lb2_corpus_fill", "lb2_corpus_scatter",
+    "lb2_strip_device_chunked", "lb2_tree_prepare", "lb2_strip_tree_ex", "lb2_tree_cleanup",
 ]
 
 
@@ -41,14 +42,14 @@ class Stats(C.Structure):
 class TreeStats(C.Structure):
     _fields_ = [
         ("n_selected", C.c_uint32), ("n_gpu", C.c_uint32), ("n_fallback", C.c_uint32), ("n_skipped", C.c_uint32),
-        ("n_failed", C.c_uint32), ("pad", C.c_uint32),
+        ("n_failed", C.c_uint32), ("n_removed", C.c_uint32),
         ("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
         ("walk_read_s", C.c_double), ("gpu_s", C.c_double), ("write_s", C.c_double), ("fallback_s", C.c_double),
         ("batch", Stats),
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("batch", "pad")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "batch"}
         d["batch"] = self.batch.as_dict()
         return d
 
@@ -118,8 +119,22 @@ def load():
     lib.lb2_corpus_fill.restype = C.c_int
     lib.lb2_corpus_scatter.argtypes = [vp, vp, vp, C.c_uint64, u64p, u64p, u64p, C.c_uint32]
     lib.lb2_corpus_scatter.restype = C.c_int
+    lib.lb2_strip_device_chunked.argtypes = [vp, vp, u64p, u64p, C.c_uint32, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp,
+                                             vp, vp, u64p, i32p, C.POINTER(Stats)]
+    lib.lb2_strip_device_chunked.restype = C.c_int
+    lib.lb2_strip_tree_ex.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint32, C.c_char_p, C.POINTER(TreeStats)]
+    lib.lb2_strip_tree_ex.restype = C.c_int
+    lib.lb2_tree_cleanup.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint32)]
+    lib.lb2_tree_cleanup.restype = C.c_int
+    lib.lb2_tree_prepare.argtypes = [vp, C.c_uint64]
+    lib.lb2_tree_prepare.restype = C.c_int
     _lib = lib
     return lib
+
+
+# consumer callback of lb2_strip_device_chunked (include/lambdipy_b200.h: lb2_chunk_fn)
+CHUNK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
+                       C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(Stats))
 
 
 class Context:

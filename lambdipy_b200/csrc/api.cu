@@ -8,19 +8,24 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cctype>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include <climits>
 #include <dirent.h>
+#include <regex.h>
 #include <fcntl.h>
 #include <spawn.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -37,8 +42,10 @@ struct Workspace {
   uint8_t *d_scratch = nullptr;
   Tile *d_tiles = nullptr;
   BatchCounters *d_ctr = nullptr;
-  uint64_t *h_stage = nullptr;  // pinned: 2*(n+1) offsets/sizes up, counters + total down
+  uint64_t *h_stage = nullptr;  // pinned: 2*(n+1) offsets/sizes up
+  uint8_t *h_res = nullptr;     // pinned: out_off[n+1] | out_size[n] | status[n] down (queued behind the kernels)
   BatchCounters *h_ctr = nullptr;
+  cudaEvent_t done = nullptr;   // recorded behind the last result copy: collect waits on this, not on the stream
   uint32_t cap_files = 0;
   uint64_t cap_tiles = 0;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -48,11 +55,14 @@ struct Workspace {
   bool in_flight = false;
 };
 
+struct TreeEngine;
 struct lb2_ctx {
   int device = 0;
+  int numa_node = -1;          // NUMA node of the GPU's PCIe root (-1: unknown / single node)
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  Workspace ws;               // lb2_strip_device_async / lb2_plan_device
+  Workspace ws;               // lb2_strip_device_async / lb2_plan_device / even chunks of lb2_strip_device_chunked
+  Workspace ws2;              // odd chunks (chunk k+1 is queued before chunk k is collected)
   std::string err;
   int compact_ctas_per_sm = 4;
   int use_tma = 1;             // bulk-copy engine kernel (0.97 of copy peak) ; LB2_COMPACT_TMA=0 selects the LSU kernel (0.90)
@@ -64,10 +74,10 @@ struct lb2_ctx {
     uint64_t cap_in = 0, cap_out = 0;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_planned = nullptr;
   } slot[3];
-  // tree: reusable pinned arenas
-  uint8_t *h_tree_in = nullptr, *h_tree_out = nullptr;
-  uint64_t cap_tree_in = 0, cap_tree_out = 0;
+  TreeEngine *tree = nullptr;  // lb2_strip_tree: pinned slot ring, I/O worker streams, HBM batch buffers
 };
+struct TreeEngine;
+static void tree_engine_free(TreeEngine *e);
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -78,6 +88,34 @@ struct lb2_ctx {
     }                                                                                              \
   } while (0)
 
+// Pinned host arenas are placed on the NUMA node the GPU hangs off: the compaction kernel of the zero-copy
+// host path reads and writes them over PCIe at ~50 GB/s per direction, and a remote-socket arena puts that
+// traffic on the inter-socket link (round 1: 40 GB/s per direction at 1 GPU, half of that per GPU at 8).
+// The policy is set only around the allocation (MPOL_PREFERRED: falls back to other nodes when full).
+static int gpu_numa_node(int device) {
+  char bus[64] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+struct NumaPreferred {
+  bool active = false;
+  explicit NumaPreferred(int node) {
+    const char *v = getenv("LB2_NUMA");
+    if (node < 0 || node >= 1024 || (v && atoi(v) == 0)) return;
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    active = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8 + 1) == 0;
+  }
+  ~NumaPreferred() { if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0); }
+};
+
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -86,8 +124,10 @@ static void ws_free(Workspace &w) {
   cudaFree(w.d_in_off); cudaFree(w.d_in_size); cudaFree(w.d_out_size); cudaFree(w.d_out_off); cudaFree(w.d_status);
   cudaFree(w.d_scratch); cudaFree(w.d_tiles); cudaFree(w.d_ctr);
   if (w.h_stage) cudaFreeHost(w.h_stage);
+  if (w.h_res) cudaFreeHost(w.h_res);
   if (w.h_ctr) cudaFreeHost(w.h_ctr);
   for (auto &e : w.ev) if (e) cudaEventDestroy(e);
+  if (w.done) cudaEventDestroy(w.done);
   w = Workspace();
 }
 
@@ -96,12 +136,16 @@ static int ws_reserve(lb2_ctx *ctx, Workspace &w, uint32_t n_files, uint64_t n_t
     CK(cudaMalloc(&w.d_ctr, sizeof(BatchCounters)));
     CK(cudaHostAlloc(&w.h_ctr, sizeof(BatchCounters) + 64, cudaHostAllocDefault));
     for (auto &e : w.ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   }
   if (n_files > w.cap_files) {
     uint32_t cap = std::max<uint32_t>(n_files, 256u);
     cap = std::max<uint32_t>(cap, w.cap_files + w.cap_files / 2);
     cudaFree(w.d_in_off); cudaFree(w.d_in_size); cudaFree(w.d_out_size); cudaFree(w.d_out_off); cudaFree(w.d_status); cudaFree(w.d_scratch);
     if (w.h_stage) cudaFreeHost(w.h_stage);
+    if (w.h_res) cudaFreeHost(w.h_res);
+    w.h_stage = nullptr; w.h_res = nullptr;
+    w.d_in_off = w.d_in_size = w.d_out_size = w.d_out_off = nullptr; w.d_status = nullptr; w.d_scratch = nullptr;
     w.cap_files = 0;
     CK(cudaMalloc(&w.d_in_off, (cap + 1) * sizeof(uint64_t)));
     CK(cudaMalloc(&w.d_in_size, (cap + 1) * sizeof(uint64_t)));
@@ -110,11 +154,13 @@ static int ws_reserve(lb2_ctx *ctx, Workspace &w, uint32_t n_files, uint64_t n_t
     CK(cudaMalloc(&w.d_status, (cap + 1) * sizeof(int32_t)));
     CK(cudaMalloc(&w.d_scratch, (uint64_t)cap * SCR_STRIDE));
     CK(cudaHostAlloc(&w.h_stage, (2ull * cap + 2) * sizeof(uint64_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&w.h_res, (2ull * cap + 2) * sizeof(uint64_t) + (cap + 1ull) * sizeof(int32_t), cudaHostAllocDefault));
     w.cap_files = cap;
   }
   if (n_tiles > w.cap_tiles) {
     uint64_t cap = std::max<uint64_t>(n_tiles, w.cap_tiles + w.cap_tiles / 2);
     cudaFree(w.d_tiles);
+    w.d_tiles = nullptr;
     w.cap_tiles = 0;
     CK(cudaMalloc(&w.d_tiles, cap * sizeof(Tile)));
     w.cap_tiles = cap;
@@ -169,7 +215,19 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
     else launch_compact(ca, ctx->sm_count * ctx->compact_ctas_per_sm, s);
   }
   CK(cudaEventRecord(w.ev[2], s));
-  CK(cudaMemcpyAsync(w.h_ctr, w.d_ctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s));
+  // results ride behind the kernels into pinned staging; collect_batch only waits for `done`, so a
+  // caller may queue the next batch (other workspace, same stream) before collecting this one
+  {
+    uint64_t *r_off = reinterpret_cast<uint64_t *>(w.h_res), *r_size = r_off + (w.cap_files + 1);
+    int32_t *r_status = reinterpret_cast<int32_t *>(r_size + (w.cap_files + 1));
+    CK(cudaMemcpyAsync(w.h_ctr, w.d_ctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(r_off, w.d_out_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (n) {
+      CK(cudaMemcpyAsync(r_size, w.d_out_size, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(r_status, w.d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(w.done, s));
+  }
   CK(cudaGetLastError());
   w.n_files = n;
   w.stream = s;
@@ -181,20 +239,19 @@ static int collect_batch(lb2_ctx *ctx, Workspace &w, uint64_t *h_out_off, uint64
                          lb2_stats *stats) {
   if (!w.in_flight) { ctx->err = "no batch in flight"; return LB2_E_STATE; }
   const uint32_t n = w.n_files;
-  cudaStream_t s = w.stream;
-  if (h_out_off) CK(cudaMemcpyAsync(h_out_off, w.d_out_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-  if (h_out_sizes && n) CK(cudaMemcpyAsync(h_out_sizes, w.d_out_size, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-  if (h_status && n) CK(cudaMemcpyAsync(h_status, w.d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  uint64_t *h_total = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(w.h_ctr) + sizeof(BatchCounters));
-  CK(cudaMemcpyAsync(h_total, w.d_out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaEventSynchronize(w.done));
   w.in_flight = false;
+  const uint64_t *r_off = reinterpret_cast<const uint64_t *>(w.h_res), *r_size = r_off + (w.cap_files + 1);
+  const int32_t *r_status = reinterpret_cast<const int32_t *>(r_size + (w.cap_files + 1));
+  if (h_out_off) memcpy(h_out_off, r_off, (size_t)(n + 1) * sizeof(uint64_t));
+  if (h_out_sizes && n) memcpy(h_out_sizes, r_size, (size_t)n * sizeof(uint64_t));
+  if (h_status && n) memcpy(h_status, r_status, (size_t)n * sizeof(int32_t));
   if (stats) {
     const BatchCounters &c = *w.h_ctr;
     memset(stats, 0, sizeof(*stats));
     stats->n_files = n; stats->n_ok = c.n_ok; stats->n_unsupported = c.n_unsupported; stats->overflow = c.overflow;
     stats->in_bytes = c.in_bytes; stats->out_bytes = c.out_bytes; stats->copy_bytes = c.copy_bytes;
-    stats->header_bytes = c.header_bytes; stats->n_tiles = c.n_tiles; stats->out_bytes_needed = *h_total;
+    stats->header_bytes = c.header_bytes; stats->n_tiles = c.n_tiles; stats->out_bytes_needed = r_off[n];
     cudaEventElapsedTime(&stats->plan_ms, w.ev[0], w.ev[1]);
     cudaEventElapsedTime(&stats->compact_ms, w.ev[1], w.ev[2]);
   }
@@ -227,6 +284,7 @@ int lb2_ctx_create(int device, lb2_ctx **out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->numa_node = gpu_numa_node(device);
   if (prop.major < 10) {
     g_create_error = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
     cudaStreamDestroy(ctx->stream);
@@ -244,6 +302,7 @@ void lb2_ctx_destroy(lb2_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   ws_free(ctx->ws);
+  ws_free(ctx->ws2);
   for (auto &sl : ctx->slot) {
     ws_free(sl.ws);
     cudaFree(sl.d_in); cudaFree(sl.d_out);
@@ -252,8 +311,7 @@ void lb2_ctx_destroy(lb2_ctx *ctx) {
     for (auto &e : sl.ev_d2h) if (e) cudaEventDestroy(e);
     if (sl.ev_planned) cudaEventDestroy(sl.ev_planned);
   }
-  if (ctx->h_tree_in) cudaFreeHost(ctx->h_tree_in);
-  if (ctx->h_tree_out) cudaFreeHost(ctx->h_tree_out);
+  tree_engine_free(ctx->tree);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -270,6 +328,7 @@ void *lb2_dev_alloc(lb2_ctx *ctx, uint64_t bytes) {
 void lb2_dev_free(lb2_ctx *, void *p) { if (p) cudaFree(p); }
 void *lb2_pinned_alloc(lb2_ctx *ctx, uint64_t bytes) {
   void *p = nullptr;
+  NumaPreferred near_gpu(ctx ? ctx->numa_node : -1);
   cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 256, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) { if (ctx) ctx->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return nullptr; }
   return p;
@@ -301,6 +360,76 @@ int lb2_plan_device(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, co
                          ctx->stream, false);
   if (rc) return rc;
   return collect_batch(ctx, ctx->ws, nullptr, h_out_sizes, h_status, stats);
+}
+
+// ---------------------------------------------------------------------------- shards larger than HBM
+// A shard whose input plus output does not fit next to each other in HBM (BASELINE config 4 on one GPU:
+// 115 GB in + 67 GB out) keeps its INPUT resident and streams the OUTPUT through a ring of two
+// slots: chunk k (consecutive files, <= max_chunk_bytes of arena span) is stripped into slot k % 2 while
+// the consumer still holds chunk k-1.  Chunk k+1 is queued on the stream before chunk k is collected, so
+// the GPU never waits for the host between chunks.
+int lb2_strip_device_chunked(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes, uint32_t n_files,
+                             void *d_out_ring, uint64_t slot_capacity, uint64_t max_chunk_bytes, uint32_t flags, void *stream,
+                             lb2_chunk_fn on_chunk, void *user, uint64_t *h_out_sizes, int32_t *h_status, lb2_stats *total_out) {
+  if (!ctx || !d_in || !h_in_off || !d_out_ring || !slot_capacity) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  if (!max_chunk_bytes || max_chunk_bytes > slot_capacity) max_chunk_bytes = slot_capacity;
+  struct Chunk { uint32_t f0, f1; };
+  std::vector<Chunk> chunks;
+  for (uint32_t f = 0; f < n_files;) {
+    uint32_t g = f + 1;
+    while (g < n_files && h_in_off[g + 1] - h_in_off[f] <= max_chunk_bytes) g++;
+    chunks.push_back({f, g});
+    f = g;
+  }
+  lb2_stats total;
+  memset(&total, 0, sizeof total);
+  total.n_files = n_files;
+  std::vector<uint64_t> coff, csz;
+  std::vector<int32_t> cst;
+  int rc = LB2_OK;
+  auto enqueue = [&](size_t k) -> int {
+    const Chunk &c = chunks[k];
+    Workspace &w = (k & 1) ? ctx->ws2 : ctx->ws;
+    uint8_t *slot = static_cast<uint8_t *>(d_out_ring) + (k & 1) * slot_capacity;
+    // offsets stay absolute inside d_in: a chunk is a window of the file list, not a copy
+    return enqueue_batch(ctx, w, static_cast<const uint8_t *>(d_in), h_in_off + c.f0, h_in_sizes ? h_in_sizes + c.f0 : nullptr,
+                         c.f1 - c.f0, slot, slot_capacity, flags, s, true);
+  };
+  auto collect = [&](size_t k) -> int {
+    const Chunk &c = chunks[k];
+    const uint32_t n = c.f1 - c.f0;
+    Workspace &w = (k & 1) ? ctx->ws2 : ctx->ws;
+    coff.resize(n + 1); csz.resize(n); cst.resize(n);
+    lb2_stats st;
+    int r = collect_batch(ctx, w, coff.data(), csz.data(), cst.data(), &st);
+    if (r) { total.out_bytes_needed = st.out_bytes_needed; total.overflow = 1; return r; }
+    if (h_out_sizes) memcpy(h_out_sizes + c.f0, csz.data(), (size_t)n * sizeof(uint64_t));
+    if (h_status) memcpy(h_status + c.f0, cst.data(), (size_t)n * sizeof(int32_t));
+    total.n_ok += st.n_ok; total.n_unsupported += st.n_unsupported; total.in_bytes += st.in_bytes; total.out_bytes += st.out_bytes;
+    total.copy_bytes += st.copy_bytes; total.header_bytes += st.header_bytes; total.n_tiles += st.n_tiles;
+    total.plan_ms += st.plan_ms; total.compact_ms += st.compact_ms;
+    if (st.out_bytes_needed > total.out_bytes_needed) total.out_bytes_needed = st.out_bytes_needed;
+    if (on_chunk) {
+      const uint8_t *slot = static_cast<const uint8_t *>(d_out_ring) + (k & 1) * slot_capacity;
+      int u = on_chunk(user, (uint32_t)k, c.f0, n, slot, coff.data(), csz.data(), cst.data(), &st);
+      if (u) { ctx->err = "chunk consumer returned " + std::to_string(u); return LB2_E_STATE; }
+    }
+    return LB2_OK;
+  };
+  for (size_t k = 0; k < chunks.size() && rc == LB2_OK; k++) {
+    if (k >= 2) rc = collect(k - 2);           // frees workspace and output slot k % 2
+    if (rc == LB2_OK) rc = enqueue(k);
+  }
+  for (size_t k = chunks.size() >= 2 ? chunks.size() - 2 : 0; k < chunks.size(); k++) {
+    Workspace &w = (k & 1) ? ctx->ws2 : ctx->ws;
+    if (!w.in_flight) continue;
+    int r = collect(k);                         // always drain what was queued
+    if (rc == LB2_OK) rc = r;
+  }
+  if (total_out) *total_out = total;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------- host pipeline
@@ -454,81 +583,106 @@ static bool ends_with(const char *s, const char *suf) {
   return a >= b && memcmp(s + a - b, suf, b) == 0;
 }
 
-struct TreeFile { std::string path; uint64_t size; mode_t mode; uint32_t times; };
+struct TreeFile { std::string path; uint64_t size; dev_t dev; ino_t ino; uint32_t times; };
+
+// The sibling lines of the reference's script (/root/reference/lambdipy/project_build.py:256-259), done on
+// the same directory walk when asked for (LB2_TREE_CLEANUP):
+//   rm -rf ROOT/*.egg-info ; rm -rf ROOT/*.dist-info                  top level, shell glob (no dot files)
+//   find ROOT/ -name __pycache__ | xargs rm -rf                        any depth, any type
+//   find ROOT/ -name tests | grep -v "PATTERN" | xargs rm -rf          PATTERN: a grep basic regex on the path
+//                                                                      line find prints ("*" keeps only paths
+//                                                                      containing a literal asterisk)
+// They run before the strip line, so shared objects under a removed directory are never stripped.
+struct Cleanup {
+  bool on = false;
+  regex_t keep;          // grep -v pattern for `tests`
+  bool have_keep = false;
+  uint32_t n_removed = 0;
+};
+
+static void rm_rf(const std::string &p) {
+  struct stat sb;
+  if (lstat(p.c_str(), &sb) != 0) return;
+  if (S_ISDIR(sb.st_mode)) {
+    if (DIR *d = opendir(p.c_str())) {
+      while (dirent *e = readdir(d)) {
+        if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+        rm_rf(p + "/" + e->d_name);
+      }
+      closedir(d);
+    }
+    rmdir(p.c_str());
+  } else {
+    unlink(p.c_str());
+  }
+}
 
 // `find ROOT/ -name "*SUFFIX"`: every directory entry whose basename matches, of any type; find does
 // not descend into symlinked directories.  What `strip` then does with each path decides the rest:
-//   regular file           -> stripped in place
-//   symlink to a file      -> the TARGET is rewritten, the link stays (so libfoo.so -> libfoo.so.1
-//                             strips libfoo.so.1 even though that name does not match)
+//   regular file           -> stripped in place: GNU strip 2.42 writes the new contents back INTO THE
+//                             EXISTING INODE (smart_rename copies), so mode, owner and every other hard
+//                             link of the file are kept -- `libfoo.so.1` hard-linked to `libfoo.so` ends up
+//                             stripped too although its name does not match
+//   symlink to a file      -> the TARGET is rewritten, the link stays
 //   directory / dangling   -> strip fails -> xargs exits 123 -> the reference's script aborts
-// A file reached through k matching paths is stripped k times by the reference; `times` keeps k.
-static void walk(const std::string &dir, const char *suffix, std::vector<TreeFile> &files, lb2_tree_stats *st) {
+// An inode reached through k matching paths (symlinks or hard links) is stripped k times by the
+// reference; `times` keeps k.  Paths are kept as found: open() follows the links like strip does.
+// `shown` is the path as find would print it (ROOT as given + "/" + relative part): what grep sees.
+static void walk(const std::string &dir, const std::string &shown, bool top, const char *suffix, Cleanup *cl,
+                 std::vector<TreeFile> &files, lb2_tree_stats *st) {
   DIR *d = opendir(dir.c_str());
   if (!d) return;
-  while (dirent *e = readdir(d)) {
-    if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
-    std::string p = dir + "/" + e->d_name;
+  std::vector<std::string> names;
+  while (dirent *e = readdir(d))
+    if (strcmp(e->d_name, ".") && strcmp(e->d_name, "..")) names.push_back(e->d_name);
+  closedir(d);
+  for (const std::string &name : names) {
+    const std::string p = dir + "/" + name, line = shown + name;
     struct stat lsb, sb;
     if (lstat(p.c_str(), &lsb) != 0) continue;
-    const bool match = ends_with(e->d_name, suffix);
-    if (match) {
+    if (cl && cl->on) {
+      bool remove = false;
+      if (top && name[0] != '.' && (ends_with(name.c_str(), ".egg-info") || ends_with(name.c_str(), ".dist-info"))) remove = true;
+      else if (name == "__pycache__") remove = true;
+      else if (name == "tests" && line.find('\n') == std::string::npos &&
+               !(cl->have_keep && regexec(&cl->keep, line.c_str(), 0, nullptr, 0) == 0)) remove = true;
+      if (remove) { rm_rf(p); cl->n_removed++; continue; }
+    }
+    if (suffix && ends_with(name.c_str(), suffix)) {
       st->n_selected++;
       if (stat(p.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) {
         st->n_failed++;  // directory, dangling link, device ...: strip errors out
       } else {
-        char real[PATH_MAX];
-        if (!realpath(p.c_str(), real)) st->n_failed++;
-        else {
-          if (S_ISLNK(lsb.st_mode)) st->n_skipped++;  // the link itself is left alone
-          files.push_back({real, (uint64_t)sb.st_size, sb.st_mode, 1});
-        }
+        if (S_ISLNK(lsb.st_mode)) st->n_skipped++;  // the link itself is left alone
+        files.push_back({p, (uint64_t)sb.st_size, sb.st_dev, sb.st_ino, 1});
       }
     }
-    if (S_ISDIR(lsb.st_mode)) walk(p, suffix, files, st);
+    if (S_ISDIR(lsb.st_mode)) walk(p, line + "/", false, suffix, cl, files, st);
   }
-  closedir(d);
+}
+
+static bool cleanup_init(Cleanup &cl, const char *keep_regex, std::string *err) {
+  cl.on = true;
+  if (keep_regex && *keep_regex) {
+    if (regcomp(&cl.keep, keep_regex, REG_NOSUB) != 0) { if (err) *err = std::string("bad keep-tests pattern: ") + keep_regex; return false; }
+    cl.have_keep = true;
+  }
+  return true;
 }
 
 static void dedupe(std::vector<TreeFile> &files) {
-  std::sort(files.begin(), files.end(), [](const TreeFile &a, const TreeFile &b) { return a.path < b.path; });
+  std::sort(files.begin(), files.end(), [](const TreeFile &a, const TreeFile &b) {
+    if (a.dev != b.dev) return a.dev < b.dev;
+    if (a.ino != b.ino) return a.ino < b.ino;
+    return a.path < b.path;
+  });
   size_t w = 0;
   for (size_t i = 0; i < files.size(); i++) {
-    if (w && files[w - 1].path == files[i].path) files[w - 1].times++;
+    if (w && files[w - 1].dev == files[i].dev && files[w - 1].ino == files[i].ino) files[w - 1].times++;
     else files[w++] = files[i];
   }
   files.resize(w);
-}
-
-// Files are read and written in <= 8 MB pieces so that one 900 MB library is handled by many I/O
-// threads instead of one (the tree of BASELINE config 3 is dominated by two such files).
-static const uint64_t IO_PIECE = 8ull << 20;
-
-static bool read_piece(const std::string &p, uint8_t *dst, uint64_t off, uint64_t n) {
-  int fd = open(p.c_str(), O_RDONLY | O_CLOEXEC);
-  if (fd < 0) return false;
-  uint64_t got = 0;
-  while (got < n) {
-    ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
-    if (r <= 0) { if (r < 0 && errno == EINTR) continue; break; }
-    got += (uint64_t)r;
-  }
-  close(fd);
-  return got == n;
-}
-
-static bool write_piece(const char *tmp, const uint8_t *src, uint64_t off, uint64_t n) {
-  int fd = open(tmp, O_WRONLY | O_CLOEXEC);
-  if (fd < 0) return false;
-  uint64_t put = 0;
-  bool ok = true;
-  while (put < n) {
-    ssize_t r = pwrite(fd, src + put, n - put, (off_t)(off + put));
-    if (r <= 0) { if (r < 0 && errno == EINTR) continue; ok = false; break; }
-    put += (uint64_t)r;
-  }
-  close(fd);
-  return ok;
+  std::sort(files.begin(), files.end(), [](const TreeFile &a, const TreeFile &b) { return a.path < b.path; });
 }
 
 static int host_strip(const std::string &p) {
@@ -543,15 +697,152 @@ static int host_strip(const std::string &p) {
 template <class F> static void parallel_for(size_t n, int threads, F f) {
   std::atomic<size_t> next{0};
   std::vector<std::thread> pool;
-  threads = (int)std::min<size_t>((size_t)threads, n);
+  threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(threads, 1), n));
   for (int t = 0; t < threads; t++)
     pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
   for (auto &th : pool) th.join();
 }
 
+// ---- the streaming engine behind lb2_strip_tree ---------------------------------------------------
+// File bytes travel   page cache --pread--> pinned slot --DMA--> HBM input arena   and back
+//                     HBM output arena --DMA--> pinned slot --pwrite--> the file's existing inode.
+// Pinned memory is only a ring of small slots (two per I/O worker, LB2_TREE_SLOT_MB each), so a
+// one-shot `lambdipy build` does not pay for pinning the tree twice and a 100 GB tree needs no more
+// host memory than a small one.  The tree is cut into batches of whole files (<= LB2_TREE_BATCH_MB of
+// arena span; a larger file is a batch of its own) that alternate between two HBM buffer sets: while
+// batch b is downloaded and written, batch b+1 is read and uploaded -- the same worker pool serves both.
+struct Seg { uint32_t file; uint64_t file_off, len, slot_off; };
+struct Slice { bool upload; uint8_t *dev; uint64_t len; uint32_t seg0, seg1; };
+
+static void make_slices(bool upload, uint8_t *dev_base, const std::vector<uint32_t> &ids, const uint64_t *offs, const uint64_t *sizes,
+                        uint64_t slot_bytes, std::vector<Seg> &segs, std::vector<Slice> &out) {
+  // ids[k] occupies [offs[k], offs[k] + sizes[k]) of the device arena, ascending and disjoint.  A slice is
+  // one contiguous DMA range of at most slot_bytes; padding between neighbouring files rides along, a
+  // larger hole (files that took another route) starts a new slice.
+  const size_t m = ids.size();
+  size_t k = 0;
+  uint64_t c = 0;  // bytes of file k already covered by earlier slices
+  while (k < m) {
+    if (sizes[k] == 0) { k++; c = 0; continue; }
+    const uint64_t a = offs[k] + c, end = a + slot_bytes;
+    Slice sl{upload, dev_base + a, 0, (uint32_t)segs.size(), 0};
+    uint64_t last = a;
+    while (k < m) {
+      if (sizes[k] == 0) { k++; c = 0; continue; }
+      const uint64_t fs = offs[k] + c, fe = offs[k] + sizes[k];
+      if (fs >= end || fs - last > 65536) break;
+      const uint64_t take = std::min(fe, end) - fs;
+      segs.push_back({ids[k], c, take, fs - a});
+      last = fs + take;
+      if (last == fe) { k++; c = 0; } else { c += take; break; }  // slot full inside a big file
+    }
+    sl.seg1 = (uint32_t)segs.size();
+    sl.len = last - a;
+    out.push_back(sl);
+  }
+}
+
+struct TreeWorker { cudaStream_t stream = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; uint32_t k = 0; };
+
+struct TreeEngine {
+  uint8_t *h_ring = nullptr;
+  uint64_t slot_bytes = 0;
+  int n_workers = 0;
+  std::vector<TreeWorker> workers;
+  uint8_t *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+  uint64_t cap_in[2] = {0, 0}, cap_out[2] = {0, 0};
+};
+
+static void tree_engine_free(TreeEngine *e) {
+  if (!e) return;
+  for (auto &w : e->workers) {
+    if (w.stream) cudaStreamDestroy(w.stream);
+    for (auto &ev : w.ev) if (ev) cudaEventDestroy(ev);
+  }
+  if (e->h_ring) cudaFreeHost(e->h_ring);
+  for (int k = 0; k < 2; k++) { cudaFree(e->d_in[k]); cudaFree(e->d_out[k]); }
+  delete e;
+}
+
+static int tree_engine_prepare(lb2_ctx *ctx, uint64_t expected_bytes) {
+  if (ctx->tree) return LB2_OK;
+  TreeEngine *e = new TreeEngine();
+  e->slot_bytes = std::max<uint64_t>(1, env_u64("LB2_TREE_SLOT_MB", 4)) << 20;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  int want = (int)env_u64("LB2_IO_THREADS", std::max(4u, std::min(32u, hw / 2)));
+  want = std::max(want, 1);
+  if (expected_bytes) want = (int)std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)want, expected_bytes / (2 * e->slot_bytes) + 1));
+  e->n_workers = want;
+  NumaPreferred near_gpu(ctx->numa_node);
+  cudaError_t err = cudaHostAlloc(&e->h_ring, (uint64_t)want * 2 * e->slot_bytes, cudaHostAllocDefault);
+  if (err != cudaSuccess) { ctx->err = std::string("cudaHostAlloc(tree ring): ") + cudaGetErrorString(err); delete e; return LB2_E_CUDA; }
+  e->workers.resize(want);
+  for (auto &w : e->workers) {
+    if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&w.ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&w.ev[1], cudaEventDisableTiming) != cudaSuccess) {
+      ctx->err = "cuda stream/event creation failed"; tree_engine_free(e); return LB2_E_CUDA;
+    }
+  }
+  ctx->tree = e;
+  return LB2_OK;
+}
+
+static bool pread_all(int fd, uint8_t *dst, uint64_t n, uint64_t off) {
+  uint64_t got = 0;
+  while (got < n) {
+    ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
+    if (r <= 0) { if (r < 0 && errno == EINTR) continue; return false; }
+    got += (uint64_t)r;
+  }
+  return true;
+}
+static bool pwrite_all(int fd, const uint8_t *src, uint64_t n, uint64_t off) {
+  uint64_t put = 0;
+  while (put < n) {
+    ssize_t r = pwrite(fd, src + put, n - put, (off_t)(off + put));
+    if (r <= 0) { if (r < 0 && errno == EINTR) continue; return false; }
+    put += (uint64_t)r;
+  }
+  return true;
+}
+
 extern "C" {
 
+int lb2_tree_prepare(lb2_ctx *ctx, uint64_t expected_tree_bytes) {
+  if (!ctx) return LB2_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = tree_engine_prepare(ctx, expected_tree_bytes);
+  if (rc) return rc;
+  // workspaces and the compaction kernel's shared-memory opt-in are first-use costs too
+  rc = ws_reserve(ctx, ctx->ws, 256, 1 << 16);
+  if (rc) return rc;
+  return ws_reserve(ctx, ctx->ws2, 256, 1 << 16);
+}
+
+int lb2_tree_cleanup(const char *root, const char *keep_tests_regex, uint32_t *n_removed) {
+  if (!root) return LB2_E_ARG;
+  struct stat rsb;
+  if (stat(root, &rsb) != 0 || !S_ISDIR(rsb.st_mode)) return LB2_E_IO;
+  Cleanup cl;
+  if (!cleanup_init(cl, keep_tests_regex, nullptr)) return LB2_E_ARG;
+  std::string r = root;
+  while (r.size() > 1 && r.back() == '/') r.pop_back();
+  std::vector<TreeFile> files;
+  lb2_tree_stats st;
+  memset(&st, 0, sizeof st);
+  walk(r, r + "/", true, nullptr, &cl, files, &st);
+  if (cl.have_keep) regfree(&cl.keep);
+  if (n_removed) *n_removed = cl.n_removed;
+  return LB2_OK;
+}
+
 int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t flags, lb2_tree_stats *st_out) {
+  return lb2_strip_tree_ex(ctx, root, suffix, flags, nullptr, st_out);
+}
+
+int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t flags, const char *keep_tests_regex,
+                      lb2_tree_stats *st_out) {
   if (!ctx || !root || !suffix) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
   CK(cudaSetDevice(ctx->device));
   lb2_tree_stats st;
@@ -562,138 +853,267 @@ int lb2_strip_tree(lb2_ctx *ctx, const char *root, const char *suffix, uint32_t 
   if (stat(root, &rsb) != 0 || !S_ISDIR(rsb.st_mode)) { ctx->err = std::string("not a directory: ") + root; return LB2_E_IO; }
   std::string r = root;
   while (r.size() > 1 && r.back() == '/') r.pop_back();
-  walk(r, suffix, files, &st);
+  Cleanup cl;
+  if ((flags & LB2_TREE_CLEANUP) && !cleanup_init(cl, keep_tests_regex, &ctx->err)) return LB2_E_ARG;
+  walk(r, r + "/", true, suffix, &cl, files, &st);
+  if (cl.have_keep) regfree(&cl.keep);
+  st.n_removed = cl.n_removed;
   dedupe(files);
   const uint32_t n = (uint32_t)files.size();
-  std::vector<uint64_t> off(n + 1), sizes(n), out_off(n + 1), out_sizes(n);
-  std::vector<int32_t> status(n);
-  uint64_t pos = 0;
-  for (uint32_t i = 0; i < n; i++) { off[i] = pos; sizes[i] = files[i].size; pos += (files[i].size + 255) & ~255ull; }
-  off[n] = pos;
-  const uint64_t in_cap = pos + 256, out_cap = pos + (uint64_t)n * 4096 + (16u << 20);
-  if (ctx->cap_tree_in < in_cap) {
-    if (ctx->h_tree_in) cudaFreeHost(ctx->h_tree_in);
-    ctx->cap_tree_in = 0;
-    CK(cudaHostAlloc(&ctx->h_tree_in, in_cap, cudaHostAllocDefault));
-    ctx->cap_tree_in = in_cap;
-  }
-  if (ctx->cap_tree_out < out_cap) {
-    if (ctx->h_tree_out) cudaFreeHost(ctx->h_tree_out);
-    ctx->cap_tree_out = 0;
-    CK(cudaHostAlloc(&ctx->h_tree_out, out_cap, cudaHostAllocDefault));
-    ctx->cap_tree_out = out_cap;
-  }
-  const int io_threads = (int)env_u64("LB2_IO_THREADS", std::max(4u, std::min(32u, std::thread::hardware_concurrency())));
-  std::atomic<int> read_fail{0};
-  struct Piece { uint32_t file; uint64_t off, len; };
-  std::vector<Piece> rpieces;
-  for (uint32_t i = 0; i < n; i++)
-    for (uint64_t o = 0; o < sizes[i] || (o == 0 && sizes[i] == 0); o += IO_PIECE) {
-      rpieces.push_back({i, o, std::min(IO_PIECE, sizes[i] - o)});
-      if (sizes[i] == 0) break;
-    }
-  parallel_for(rpieces.size(), io_threads, [&](size_t k) {
-    const Piece &pc = rpieces[k];
-    if (pc.len && !read_piece(files[pc.file].path, ctx->h_tree_in + off[pc.file] + pc.off, pc.off, pc.len)) read_fail++;
-  });
-  if (read_fail) { ctx->err = "could not read some selected files"; return LB2_E_IO; }
+  uint64_t tree_bytes = 0;
+  for (auto &f : files) tree_bytes += f.size;
   st.walk_read_s = now_s() - t0;
+  if (!n) { if (st_out) *st_out = st; return LB2_OK; }
+  int rc = tree_engine_prepare(ctx, tree_bytes);
+  if (rc) return rc;
+  TreeEngine &E = *ctx->tree;
+  const bool dry = (flags & LB2_TREE_DRY_RUN) != 0;
 
-  t0 = now_s();
-  int rc = LB2_OK;
-  if (n) rc = lb2_strip_host(ctx, ctx->h_tree_in, off.data(), sizes.data(), n, ctx->h_tree_out, ctx->cap_tree_out, out_off.data(),
-                             out_sizes.data(), status.data(), flags & 0xffu, &st.batch);
-  // files the reference would strip more than once (reached through several matching names):
-  // run the extra passes on the previous pass's output (strip is not always idempotent)
-  for (uint32_t pass = 1; rc == LB2_OK; pass++) {
-    std::vector<uint32_t> again;
-    for (uint32_t i = 0; i < n; i++) if (files[i].times > pass && status[i] == LB2_ST_OK) again.push_back(i);
-    if (again.empty()) break;
-    const uint32_t m = (uint32_t)again.size();
-    std::vector<uint64_t> off2(m + 1), sz2(m), ooff2(m + 1), osz2(m);
-    std::vector<int32_t> st2(m);
-    uint64_t p2 = 0;
-    for (uint32_t k = 0; k < m; k++) { off2[k] = p2; sz2[k] = out_sizes[again[k]]; p2 += (sz2[k] + 255) & ~255ull; }
-    off2[m] = p2;
-    // previous outputs become inputs (the input arena is free to reuse: it is at least as large)
-    for (uint32_t k = 0; k < m; k++) memcpy(ctx->h_tree_in + off2[k], ctx->h_tree_out + out_off[again[k]], sz2[k]);
-    std::vector<uint8_t> keep_out;  // outputs of files not in this pass stay where they are; new ones go to a scratch arena
-    uint8_t *h_tmp = nullptr;
-    const uint64_t cap2 = p2 + (uint64_t)m * 4096 + (16u << 20);
-    CK(cudaHostAlloc(&h_tmp, cap2, cudaHostAllocDefault));
-    lb2_stats b2;
-    rc = lb2_strip_host(ctx, ctx->h_tree_in, off2.data(), sz2.data(), m, h_tmp, cap2, ooff2.data(), osz2.data(), st2.data(), flags & 0xffu, &b2);
-    if (rc == LB2_OK) {
-      for (uint32_t k = 0; k < m; k++) {
-        const uint32_t i = again[k];
-        if (st2[k] != LB2_ST_OK) { status[i] = st2[k]; continue; }
-        // a re-stripped file never grows beyond its 256-byte-rounded slot by more than the slack between files
-        if (osz2[k] <= ((out_sizes[i] + 255) & ~255ull)) { memcpy(ctx->h_tree_out + out_off[i], h_tmp + ooff2[k], osz2[k]); out_sizes[i] = osz2[k]; }
-        else status[i] = LB2_ST_UNSUPPORTED_LAYOUT;  // hand to the host strip
+  // ---- batches of whole files
+  const uint64_t batch_bytes = std::max<uint64_t>(1, env_u64("LB2_TREE_BATCH_MB", 1024)) << 20;
+  struct Batch { uint32_t f0, f1; uint64_t span; };
+  std::vector<Batch> batches;
+  std::vector<uint64_t> off(n + 1), sizes(n), out_off(n + 1), out_sizes(n);  // offsets are relative to the batch's arena
+  std::vector<int32_t> status(n, LB2_ST_MALFORMED);
+  for (uint32_t f = 0; f < n;) {
+    uint64_t pos = 0;
+    uint32_t g = f;
+    while (g < n && (g == f || pos + ((files[g].size + 255) & ~255ull) <= batch_bytes)) {
+      off[g] = pos; sizes[g] = files[g].size; pos += (files[g].size + 255) & ~255ull; g++;
+    }
+    batches.push_back({f, g, pos});
+    f = g;
+  }
+
+  // ---- worker pool: one task queue served by n_workers threads, each with two pinned slots + a stream
+  std::vector<Seg> segs;
+  std::vector<Slice> queue;
+  std::atomic<size_t> q_next{0}, q_done{0};
+  size_t q_end = 0;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  bool quit = false;
+  std::atomic<int> io_fail{0};
+  std::vector<std::atomic<int>> read_bad(n), write_bad(n);
+  std::vector<std::atomic<uint32_t>> segs_left(n);
+  for (uint32_t i = 0; i < n; i++) { read_bad[i] = 0; write_bad[i] = 0; segs_left[i] = 0; }
+  std::atomic<uint32_t> n_gpu{0}, n_failed{0}, n_skipped{0};
+  std::atomic<uint64_t> in_b{0}, out_b{0};
+  std::vector<uint64_t> final_size(n, 0);
+
+  auto finish_file = [&](uint32_t i) {
+    // every piece of the new contents is in the inode: cut the old tail off
+    bool ok = write_bad[i] == 0;
+    if (ok && final_size[i] != files[i].size) ok = truncate(files[i].path.c_str(), (off_t)final_size[i]) == 0;
+    if (ok) { n_gpu++; in_b += files[i].size; out_b += final_size[i]; }
+    else n_failed++;
+  };
+  auto run_slice = [&](TreeWorker &w, int widx, const Slice &sl) {
+    uint8_t *slot = E.h_ring + ((uint64_t)widx * 2 + (w.k & 1)) * E.slot_bytes;
+    cudaEvent_t ev = w.ev[w.k & 1];
+    w.k++;
+    if (sl.upload) {
+      cudaEventSynchronize(ev);  // the DMA that last read this slot has finished
+      for (uint32_t q = sl.seg0; q < sl.seg1; q++) {
+        const Seg &sg = segs[q];
+        int fd = open(files[sg.file].path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0 || !pread_all(fd, slot + sg.slot_off, sg.len, sg.file_off)) { read_bad[sg.file]++; io_fail++; }
+        if (fd >= 0) close(fd);
+      }
+      cudaMemcpyAsync(sl.dev, slot, sl.len, cudaMemcpyHostToDevice, w.stream);
+      cudaEventRecord(ev, w.stream);
+    } else {
+      cudaMemcpyAsync(slot, sl.dev, sl.len, cudaMemcpyDeviceToHost, w.stream);
+      cudaEventRecord(ev, w.stream);
+      if (cudaEventSynchronize(ev) != cudaSuccess) io_fail++;
+      for (uint32_t q = sl.seg0; q < sl.seg1; q++) {
+        const Seg &sg = segs[q];
+        // no O_TRUNC, no temp file: the bytes go into the pages the file already has (see walk())
+        int fd = open(files[sg.file].path.c_str(), O_WRONLY | O_CLOEXEC);
+        if (fd < 0 || !pwrite_all(fd, slot + sg.slot_off, sg.len, sg.file_off)) write_bad[sg.file]++;
+        if (fd >= 0) close(fd);
+        if (--segs_left[sg.file] == 0) finish_file(sg.file);
       }
     }
-    cudaFreeHost(h_tmp);
+  };
+  std::vector<std::thread> pool;
+  for (int wi = 0; wi < E.n_workers; wi++)
+    pool.emplace_back([&, wi] {
+      cudaSetDevice(ctx->device);
+      TreeWorker &w = E.workers[wi];
+      for (;;) {
+        size_t idx;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv_work.wait(lk, [&] { return quit || q_next.load() < q_end; });
+          if (q_next.load() >= q_end) { if (quit) return; continue; }
+          idx = q_next.fetch_add(1);
+        }
+        run_slice(w, wi, queue[idx]);
+        if (q_done.fetch_add(1) + 1 == q_end) { std::lock_guard<std::mutex> lk(mu); cv_done.notify_all(); }
+      }
+    });
+  auto submit_and_wait = [&](std::vector<Slice> &a, std::vector<Slice> &b) {
+    // interleave the two task lists so that downloads of batch b and uploads of batch b+1 overlap
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      size_t i = 0, j = 0;
+      while (i < a.size() || j < b.size()) {
+        if (i < a.size()) queue.push_back(a[i++]);
+        if (j < b.size()) queue.push_back(b[j++]);
+      }
+      q_end = queue.size();
+    }
+    cv_work.notify_all();
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return q_done.load() >= q_end; });
+  };
+  auto stop_pool = [&] {
+    { std::lock_guard<std::mutex> lk(mu); quit = true; }
+    cv_work.notify_all();
+    for (auto &th : pool) th.join();
+  };
+
+  auto upload_slices = [&](size_t bi, std::vector<Slice> &out) -> int {
+    const Batch &b = batches[bi];
+    const int set = (int)(bi & 1);
+    if (E.cap_in[set] < b.span + 256) {
+      cudaFree(E.d_in[set]); E.d_in[set] = nullptr; E.cap_in[set] = 0;
+      const uint64_t need = b.span + 256;
+      CK(cudaMalloc(&E.d_in[set], need));
+      E.cap_in[set] = need;
+    }
+    std::vector<uint32_t> ids(b.f1 - b.f0);
+    for (uint32_t i = b.f0; i < b.f1; i++) ids[i - b.f0] = i;
+    make_slices(true, E.d_in[set], ids, off.data() + b.f0, sizes.data() + b.f0, E.slot_bytes, segs, out);
+    return LB2_OK;
+  };
+
+  std::vector<void *> tmp_dev;  // outputs of the re-strip passes, freed at the end
+  std::vector<Slice> up, down, none;
+  double t_gpu = 0, t_io0 = now_s();
+  // (a lambda so that every CUDA error path still reaches stop_pool() below)
+  auto run_batches = [&]() -> int {
+  int rc = upload_slices(0, up);
+  if (rc == LB2_OK) submit_and_wait(up, none);
+  for (size_t bi = 0; bi < batches.size() && rc == LB2_OK; bi++) {
+    const Batch &b = batches[bi];
+    const int set = (int)(bi & 1);
+    const uint32_t m = b.f1 - b.f0;
+    bool bad_read = false;
+    for (uint32_t i = b.f0; i < b.f1; i++) bad_read |= read_bad[i] != 0;
+    if (bad_read) { ctx->err = "could not read some selected files"; rc = LB2_E_IO; break; }
+    // ---- kernels on the batch, inputs in HBM
+    const double tg = now_s();
+    for (auto &w : E.workers) { CK(cudaStreamWaitEvent(ctx->stream, w.ev[0], 0)); CK(cudaStreamWaitEvent(ctx->stream, w.ev[1], 0)); }
+    uint64_t want_out = b.span + (uint64_t)m * 4096 + (16u << 20);
+    Workspace &ws = set ? ctx->ws2 : ctx->ws;
+    lb2_stats bst;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (E.cap_out[set] < want_out) {
+        cudaFree(E.d_out[set]); E.d_out[set] = nullptr; E.cap_out[set] = 0;
+        CK(cudaMalloc(&E.d_out[set], want_out));
+        E.cap_out[set] = want_out;
+      }
+      rc = enqueue_batch(ctx, ws, E.d_in[set], off.data() + b.f0, sizes.data() + b.f0, m, E.d_out[set], E.cap_out[set], flags & 0xffu, ctx->stream, true);
+      if (rc) break;
+      rc = collect_batch(ctx, ws, out_off.data() + b.f0, out_sizes.data() + b.f0, status.data() + b.f0, &bst);
+      if (rc != LB2_E_CAPACITY) break;
+      want_out = bst.out_bytes_needed + (1u << 20);  // re-laid-out files can grow: enlarge and redo
+    }
+    if (rc) break;
+    st.batch.n_files += m; st.batch.n_ok += bst.n_ok; st.batch.n_unsupported += bst.n_unsupported; st.batch.in_bytes += bst.in_bytes;
+    st.batch.out_bytes += bst.out_bytes; st.batch.copy_bytes += bst.copy_bytes; st.batch.header_bytes += bst.header_bytes;
+    st.batch.n_tiles += bst.n_tiles; st.batch.plan_ms += bst.plan_ms; st.batch.compact_ms += bst.compact_ms;
+    // ---- inodes the reference strips more than once (several matching names): further passes run on
+    //      the previous pass's output, still in HBM (strip is not idempotent on a few note layouts)
+    std::vector<uint8_t *> src_base(m, E.d_out[set]);
+    std::vector<uint64_t> src_off(out_off.begin() + b.f0, out_off.begin() + b.f1);
+    for (uint32_t pass = 1; rc == LB2_OK; pass++) {
+      std::vector<uint32_t> again;
+      for (uint32_t i = b.f0; i < b.f1; i++) if (files[i].times > pass && status[i] == LB2_ST_OK) again.push_back(i);
+      if (again.empty()) break;
+      const uint32_t k2 = (uint32_t)again.size();
+      std::vector<uint64_t> off2(k2 + 1), sz2(k2), ooff2(k2 + 1), osz2(k2);
+      std::vector<int32_t> st2(k2);
+      uint64_t p2 = 0;
+      for (uint32_t k = 0; k < k2; k++) { off2[k] = p2; sz2[k] = out_sizes[again[k]]; p2 += (sz2[k] + 255) & ~255ull; }
+      off2[k2] = p2;
+      uint8_t *d_in2 = nullptr, *d_out2 = nullptr;
+      const uint64_t cap2 = p2 + (uint64_t)k2 * 4096 + (64u << 20);
+      CK(cudaMalloc(&d_in2, p2 + 256));
+      tmp_dev.push_back(d_in2);
+      CK(cudaMalloc(&d_out2, cap2));
+      tmp_dev.push_back(d_out2);
+      for (uint32_t k = 0; k < k2; k++) {
+        const uint32_t i = again[k];
+        CK(cudaMemcpyAsync(d_in2 + off2[k], src_base[i - b.f0] + src_off[i - b.f0], sz2[k], cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      lb2_stats b2;
+      rc = enqueue_batch(ctx, ws, d_in2, off2.data(), sz2.data(), k2, d_out2, cap2, flags & 0xffu, ctx->stream, true);
+      if (rc == LB2_OK) rc = collect_batch(ctx, ws, ooff2.data(), osz2.data(), st2.data(), &b2);
+      if (rc == LB2_E_CAPACITY) { rc = LB2_OK; for (auto &x : st2) x = LB2_ST_UNSUPPORTED_LAYOUT; }  // hand them to the host strip
+      if (rc) break;
+      for (uint32_t k = 0; k < k2; k++) {
+        const uint32_t i = again[k];
+        status[i] = st2[k];
+        if (st2[k] != LB2_ST_OK) continue;
+        src_base[i - b.f0] = d_out2; src_off[i - b.f0] = ooff2[k]; out_sizes[i] = osz2[k];
+      }
+    }
+    if (rc) break;
+    t_gpu += now_s() - tg;
+    // ---- download + write this batch, read + upload the next one
+    down.clear(); up.clear();
+    if (!dry) {
+      // group by source buffer so that slices stay contiguous DMA ranges
+      std::vector<uint8_t *> bases;
+      for (uint32_t i = 0; i < m; i++) if (std::find(bases.begin(), bases.end(), src_base[i]) == bases.end()) bases.push_back(src_base[i]);
+      for (uint8_t *base : bases) {
+        std::vector<std::pair<uint64_t, uint32_t>> ord;
+        for (uint32_t i = 0; i < m; i++)
+          if (src_base[i] == base && status[b.f0 + i] == LB2_ST_OK) ord.push_back({src_off[i], b.f0 + i});
+        std::sort(ord.begin(), ord.end());
+        std::vector<uint32_t> ids;
+        std::vector<uint64_t> o2, s2;
+        for (auto &pr : ord) { ids.push_back(pr.second); o2.push_back(pr.first); s2.push_back(out_sizes[pr.second]); }
+        const size_t seg_before = segs.size();
+        make_slices(false, base, ids, o2.data(), s2.data(), E.slot_bytes, segs, down);
+        for (size_t q = seg_before; q < segs.size(); q++) segs_left[segs[q].file]++;
+        for (auto &pr : ord) {
+          final_size[pr.second] = out_sizes[pr.second];
+          if (out_sizes[pr.second] == 0) finish_file(pr.second);  // (cannot happen for a valid ELF; keeps the accounting total)
+        }
+      }
+    } else {
+      for (uint32_t i = b.f0; i < b.f1; i++) if (status[i] == LB2_ST_OK) { n_gpu++; in_b += files[i].size; out_b += out_sizes[i]; }
+    }
+    if (bi + 1 < batches.size()) rc = upload_slices(bi + 1, up);
+    if (rc) break;
+    submit_and_wait(down, up);
   }
-  st.gpu_s = now_s() - t0;
+  return rc;
+  };
+  rc = run_batches();
+  stop_pool();
+  cudaStreamSynchronize(ctx->stream);
+  for (void *p : tmp_dev) cudaFree(p);
+  st.gpu_s = t_gpu;
+  st.write_s = now_s() - t_io0 - t_gpu;  // read/upload and download/write overlap: I/O wall time next to the kernels
   if (rc) { if (st_out) *st_out = st; return rc; }
 
   t0 = now_s();
-  std::atomic<uint32_t> n_gpu{0}, n_failed{0}, n_skipped{0};
-  std::atomic<uint64_t> in_b{0}, out_b{0};
   std::vector<uint32_t> fallback;
   for (uint32_t i = 0; i < n; i++) if (status[i] != LB2_ST_OK) fallback.push_back(i);
-  if (!(flags & LB2_TREE_DRY_RUN)) {
-    // temp file next to the target (pre-sized), pieces written in parallel, then fchmod + rename by
-    // whichever thread finishes the file's last piece -- what strip does, minus the single thread
-    std::vector<std::string> tmp_path(n);
-
-    std::vector<std::atomic<int>> remaining(n);
-    std::vector<std::atomic<int>> piece_fail(n);
-    std::vector<Piece> wpieces;
-    for (uint32_t i = 0; i < n; i++) {
-      remaining[i] = 0; piece_fail[i] = 0;
-      if (status[i] != LB2_ST_OK) continue;
-      std::string t = files[i].path + ".lb2XXXXXX";
-      std::vector<char> tb(t.begin(), t.end());
-      tb.push_back(0);
-      int fd = mkstemp(tb.data());
-      if (fd < 0) { n_failed++; continue; }
-      if (ftruncate(fd, (off_t)out_sizes[i]) != 0) { close(fd); unlink(tb.data()); n_failed++; continue; }
-      close(fd);
-      tmp_path[i] = tb.data();
-      int cnt = 0;
-      for (uint64_t o = 0; o < out_sizes[i]; o += IO_PIECE) { wpieces.push_back({i, o, std::min(IO_PIECE, out_sizes[i] - o)}); cnt++; }
-      if (cnt == 0) { wpieces.push_back({i, 0, 0}); cnt = 1; }
-      remaining[i] = cnt;
-    }
-    parallel_for(wpieces.size(), io_threads, [&](size_t k) {
-      const Piece &pc = wpieces[k];
-      const uint32_t i = pc.file;
-      // (pieces of one file still serialise on the inode lock inside the kernel -- measured: a shared
-      //  mmap is no faster on tmpfs -- but pieces of different files, and all reads, run in parallel)
-      if (pc.len && !write_piece(tmp_path[i].c_str(), ctx->h_tree_out + out_off[i] + pc.off, pc.off, pc.len)) piece_fail[i]++;
-      if (--remaining[i] == 0) {
-        bool ok = piece_fail[i] == 0 && chmod(tmp_path[i].c_str(), files[i].mode & 07777) == 0 &&
-                  rename(tmp_path[i].c_str(), files[i].path.c_str()) == 0;
-        if (ok) { n_gpu++; in_b += sizes[i]; out_b += out_sizes[i]; }
-        else { unlink(tmp_path[i].c_str()); n_failed++; }
-      }
-    });
-  } else {
-    for (uint32_t i = 0; i < n; i++) if (status[i] == LB2_ST_OK) { n_gpu++; in_b += sizes[i]; out_b += out_sizes[i]; }
-  }
-  st.write_s = now_s() - t0;
-
-  t0 = now_s();
   std::atomic<uint32_t> n_fb{0};
-  parallel_for(fallback.size(), io_threads, [&](size_t k) {
+  parallel_for(fallback.size(), E.n_workers, [&](size_t k) {
     const uint32_t i = fallback[k];
     const bool non_elf = status[i] == LB2_ST_NOT_ELF;
     if (non_elf && (flags & LB2_TREE_TOLERATE_NON_ELF)) { n_skipped++; return; }
-    if ((flags & LB2_TREE_FALLBACK_HOST_STRIP) && !(flags & LB2_TREE_DRY_RUN)) {
+    if ((flags & LB2_TREE_FALLBACK_HOST_STRIP) && !dry) {
       // the reference's own tool decides (and fails the build exactly when the reference would)
       bool ok = true;
-      for (uint32_t k = 0; k < files[i].times && ok; k++) ok = host_strip(files[i].path) == 0;
+      for (uint32_t q = 0; q < files[i].times && ok; q++) ok = host_strip(files[i].path) == 0;
       if (ok) n_fb++; else n_failed++;
     } else {
       n_failed++;

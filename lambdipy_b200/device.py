@@ -12,14 +12,25 @@ def _u64p(a):
 
 
 class DeviceBatch:
-    def __init__(self, ctx, off, sizes, out_slack=None):
-        """off: uint64[n+1] arena offsets (multiples of 256), sizes: uint64[n] exact sizes."""
+    def __init__(self, ctx, off, sizes, out_slack=None, chunk_bytes=None):
+        """off: uint64[n+1] arena offsets (multiples of 256), sizes: uint64[n] exact sizes.
+        chunk_bytes: keep only the INPUT resident and stream the output through two slots of that
+        many bytes (+ slack) -- for shards whose input + output exceed HBM (lb2_strip_device_chunked)."""
         self.ctx = ctx
         self.n = len(sizes)
         self.off = np.ascontiguousarray(off, dtype=np.uint64)
         self.sizes = np.ascontiguousarray(sizes if self.n else np.zeros(1), dtype=np.uint64)
         self.in_bytes = int(self.off[-1]) + 256
-        self.out_cap = self.in_bytes + self.n * 4096 + (16 << 20) if out_slack is None else self.in_bytes + out_slack
+        self.chunk_bytes = chunk_bytes
+        if chunk_bytes is None:
+            self.out_cap = self.in_bytes + self.n * 4096 + (16 << 20) if out_slack is None else self.in_bytes + out_slack
+            self.d_out = None
+        else:
+            # a chunk holds whole files: at least the largest file, plus growth slack per file
+            biggest = int(((self.sizes + np.uint64(255)) // np.uint64(256) * np.uint64(256)).max()) if self.n else 0
+            self.chunk_bytes = max(int(chunk_bytes), biggest)
+            self.slot_cap = self.chunk_bytes + min(self.n, 1 << 16) * 4096 + (16 << 20)
+            self.out_cap = 2 * self.slot_cap
         self.d_in = ctx.dev_alloc(self.in_bytes)
         self.d_out = ctx.dev_alloc(self.out_cap)
         self.out_off = np.zeros(self.n + 1, dtype=np.uint64)
@@ -27,8 +38,8 @@ class DeviceBatch:
         self.status = np.zeros(max(self.n, 1), dtype=np.int32)
 
     @classmethod
-    def from_corpus(cls, ctx, corpus):
-        b = cls(ctx, corpus.off, corpus.sizes)
+    def from_corpus(cls, ctx, corpus, chunk_bytes=None):
+        b = cls(ctx, corpus.off, corpus.sizes, chunk_bytes=chunk_bytes)
         ctx.check(ctx.lib.lb2_memset_d(ctx.h, b.d_in, 0, b.in_bytes))
         regs = corpus.fill_regions()
         if len(regs):
@@ -62,6 +73,22 @@ class DeviceBatch:
         st = N.Stats()
         self.ctx.check(self.ctx.lib.lb2_batch_results(self.ctx.h, _u64p(self.out_off), _u64p(self.out_sizes),
                                                       self.status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return st.as_dict()
+
+    def strip_chunked(self, flags=0, stream=None, on_chunk=None):
+        """One pass over the shard with the output streamed through the two-slot ring.  on_chunk(chunk,
+        first_file, n_files, d_slot, out_off, out_sizes, status) is called while the chunk's slot is valid."""
+        st = N.Stats()
+        cb = None
+        if on_chunk is not None:
+            def _cb(user, chunk, f0, n, d_slot, ooff, osz, stat, cst):
+                on_chunk(chunk, f0, n, d_slot, np.ctypeslib.as_array(ooff, (n + 1,)), np.ctypeslib.as_array(osz, (n,)),
+                         np.ctypeslib.as_array(stat, (n,)))
+                return 0
+            cb = N.CHUNK_FN(_cb)
+        self.ctx.check(self.ctx.lib.lb2_strip_device_chunked(
+            self.ctx.h, self.d_in, _u64p(self.off), _u64p(self.sizes), self.n, self.d_out, self.slot_cap, self.chunk_bytes, flags, stream,
+            C.cast(cb, C.c_void_p) if cb else None, None, _u64p(self.out_sizes), self.status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
         return st.as_dict()
 
     def read_input(self, i):

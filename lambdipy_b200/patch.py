@@ -6,6 +6,7 @@ Only `install_non_resolved_requirements` is replaced -- in lambdipy.project_buil
 lambdipy.cli, which imported the name (/root/reference/lambdipy/cli.py:11-16).  `lambdipy build`,
 its options, PackageBuild and every other function keep running the reference's own code.
 """
+import os
 import sys
 
 
@@ -15,6 +16,13 @@ def apply():
     from . import project_build as mine
     ref.install_non_resolved_requirements = mine.install_non_resolved_requirements
     cli.install_non_resolved_requirements = mine.install_non_resolved_requirements
+    # `lambdipy build` spends seconds resolving, downloading and copying packages before it reaches the
+    # strip step (cli.py:52-67): create the CUDA context behind that, not in front of the strip
+    if os.environ.get("LAMBDIPY_B200_EAGER_WARMUP", "1") != "0":
+        try:
+            mine.warmup()
+        except ValueError:
+            pass
     return cli
 
 

@@ -84,12 +84,16 @@ def strip_buffers(ctx, blobs, flags=0, out_slack=None):
         ctx.pinned_free(out_ptr)
 
 
-def strip_tree(root, suffix=".so", device=0, fallback_host_strip=True, tolerate_non_elf=False, dry_run=False, ctx=None):
+def strip_tree(root, suffix=".so", device=0, fallback_host_strip=True, tolerate_non_elf=False, dry_run=False, ctx=None,
+               cleanup=False, keep_tests_regex=None):
     """Strip every `*{suffix}` regular file under `root` in place.  Returns the tree statistics.
 
     Selection and side effects follow the reference pipeline (basename match, symlinks and
-    directories left alone, file mode kept, temp file + rename).  `n_failed > 0` corresponds to the
-    reference script exiting non-zero (xargs rc 123)."""
+    directories left alone, new contents written into the existing inode like GNU strip 2.42: mode,
+    owner and other hard links kept).  `n_failed > 0` corresponds to the reference script exiting
+    non-zero (xargs rc 123).  cleanup=True also performs the script's three `rm -rf` lines
+    (/root/reference/lambdipy/project_build.py:256-259) on the same walk; keep_tests_regex is the
+    `grep -v` pattern of the `tests` line ("*" when the reference's keep_tests is None)."""
     own = ctx is None
     if own:
         ctx = N.Context(device)
@@ -101,9 +105,22 @@ def strip_tree(root, suffix=".so", device=0, fallback_host_strip=True, tolerate_
             flags |= N.TREE_TOLERATE_NON_ELF
         if dry_run:
             flags |= N.TREE_DRY_RUN
+        if cleanup:
+            flags |= N.TREE_CLEANUP
         st = N.TreeStats()
-        ctx.check(ctx.lib.lb2_strip_tree(ctx.h, os.fsencode(root), os.fsencode(suffix), flags, C.byref(st)))
+        kr = None if keep_tests_regex is None else os.fsencode(keep_tests_regex)
+        ctx.check(ctx.lib.lb2_strip_tree_ex(ctx.h, os.fsencode(root), os.fsencode(suffix), flags, kr, C.byref(st)))
         return st.as_dict()
     finally:
         if own:
             ctx.close()
+
+
+def cleanup_tree(root, keep_tests_regex="*"):
+    """Only the clean-up lines of the reference's script (project_build.py:256-259); needs no GPU."""
+    lib = N.load()
+    n = C.c_uint32()
+    rc = lib.lb2_tree_cleanup(os.fsencode(root), None if keep_tests_regex is None else os.fsencode(keep_tests_regex), C.byref(n))
+    if rc != N.LB2_OK:
+        raise N.NativeError(rc, "lb2_tree_cleanup(%r)" % root)
+    return n.value

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--files-per-gpu", "96", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--total-files", "96", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]

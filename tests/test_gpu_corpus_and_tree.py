@@ -176,3 +176,86 @@ def test_strip_tree_failure_and_tolerance(gpu_ctx, variants, tmp_path):
     os.makedirs(empty)
     st = S.strip_tree(empty, ctx=gpu_ctx)
     assert st["n_selected"] == 0 and st["n_failed"] == 0     # documented deviation: xargs would run `strip` with no args (rc 123)
+
+
+def _tree_meta(root):
+    out = {}
+    for d, dirs, fs in os.walk(root):
+        for f in fs:
+            p = os.path.join(d, f)
+            if not os.path.islink(p):
+                st = os.stat(p)
+                out[os.path.relpath(p, root)] = (st.st_nlink, st.st_mode & 0o7777, st.st_uid)
+    return out
+
+
+def test_strip_tree_hard_links_keep_the_inode_like_strip_2_42(gpu_ctx, variants, tmp_path):
+    """GNU strip 2.42 writes the stripped bytes back into the existing inode: a hard link whose name does not match
+    is stripped too, two matching hard links mean the inode is stripped twice, link counts and modes survive."""
+    from lambdipy_b200 import strip as S
+
+    def mk(root):
+        os.makedirs(os.path.join(root, "pkg"))
+        shutil.copy(variants["c_g"], os.path.join(root, "pkg", "liba.so"))
+        os.link(os.path.join(root, "pkg", "liba.so"), os.path.join(root, "pkg", "liba.so.1"))        # other name does not match
+        shutil.copy(variants["cxx_g"], os.path.join(root, "pkg", "libb.so"))
+        os.link(os.path.join(root, "pkg", "libb.so"), os.path.join(root, "libb_alias.so"))           # both names match
+        shutil.copy(variants["c_gold"], os.path.join(root, "pkg", "ro.so"))
+        os.chmod(os.path.join(root, "pkg", "ro.so"), 0o640)
+
+    a, b = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    mk(a); mk(b)
+    inodes_before = {k: os.stat(os.path.join(b, k)).st_ino for k in _tree_meta(b)}
+    rc = subprocess.run(["bash", "-c", 'find %s/ -name "*.so" | xargs strip' % a], capture_output=True)
+    assert rc.returncode == 0, rc.stderr
+    st = S.strip_tree(b, ctx=gpu_ctx)
+    assert st["n_failed"] == 0 and st["n_fallback"] == 0 and st["n_gpu"] == 3 and st["n_selected"] == 4
+    assert _snapshot(a) == _snapshot(b)
+    assert _tree_meta(a) == _tree_meta(b)
+    assert {k: os.stat(os.path.join(b, k)).st_ino for k in _tree_meta(b)} == inodes_before   # same inodes as before the call
+    with open(os.path.join(b, "pkg", "liba.so.1"), "rb") as f1, open(os.path.join(b, "pkg", "liba.so"), "rb") as f2:
+        assert f1.read() == f2.read() and os.path.getsize(os.path.join(b, "pkg", "liba.so")) < os.path.getsize(variants["c_g"])
+
+
+def test_strip_tree_with_cleanup_equals_reference_script(gpu_ctx, variants, tmp_path):
+    """LB2_TREE_CLEANUP: the script's rm lines (:256-259) and the strip line (:260) on one walk == the reference's lines."""
+    from lambdipy_b200 import strip as S
+
+    def mk(root):
+        for sub in ("pkg", "pkg/tests", "pkg/__pycache__", "numpy/tests", "x-1.0.dist-info"):
+            os.makedirs(os.path.join(root, sub))
+        shutil.copy(variants["c_g"], os.path.join(root, "pkg", "m.so"))
+        shutil.copy(variants["cxx_g"], os.path.join(root, "pkg", "tests", "helper.so"))     # removed with its directory, never stripped
+        shutil.copy(variants["c_gold"], os.path.join(root, "numpy", "tests", "kept.so"))    # kept by the pattern -> stripped
+        with open(os.path.join(root, "pkg", "__pycache__", "m.pyc"), "w") as f:
+            f.write("x")
+
+    a, b = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    mk(a); mk(b)
+    script = "\n".join(["set -ex", "rm -rf %s/*.egg-info" % a, "rm -rf %s/*.dist-info" % a, "find %s/ -name __pycache__ | xargs rm -rf" % a,
+                        'find %s/ -name tests | grep -v "numpy" | xargs rm -rf' % a, 'find %s/ -name "*.so" | xargs strip' % a])
+    assert subprocess.run(["bash", "-c", script], capture_output=True).returncode == 0
+    st = S.strip_tree(b, ctx=gpu_ctx, cleanup=True, keep_tests_regex="numpy")
+    assert st["n_removed"] == 3 and st["n_gpu"] == 2 and st["n_failed"] == 0
+    assert _snapshot(a) == _snapshot(b)
+    assert sorted(os.listdir(b)) == ["numpy", "pkg"] and os.listdir(os.path.join(b, "pkg")) == ["m.so"]
+
+
+def test_strip_tree_streams_in_batches(gpu_ctx, tmp_path, monkeypatch):
+    """Tiny batches and slots force the multi-batch path (upload of batch b+1 overlapping the download of batch b,
+    files split over several slices) on the real wheels: the result is still the reference's tree."""
+    from lambdipy_b200 import _native as N
+    from lambdipy_b200 import strip as S
+    monkeypatch.setenv("LB2_TREE_BATCH_MB", "8")
+    monkeypatch.setenv("LB2_TREE_SLOT_MB", "1")
+    monkeypatch.setenv("LB2_IO_THREADS", "3")
+    a, b = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    os.makedirs(a); os.makedirs(b)
+    _copy_tree(a); _copy_tree(b)
+    rc = subprocess.run(["bash", "-c", 'find %s/ -name "*.so" | xargs strip' % a], capture_output=True)
+    assert rc.returncode == 0, rc.stderr
+    with N.Context(0) as ctx:       # a fresh context: the slot ring is sized at first use
+        st = S.strip_tree(b, ctx=ctx)
+    assert st["n_failed"] == 0 and st["n_fallback"] == 0
+    sa, sb = _snapshot(a), _snapshot(b)
+    assert sa == sb
