@@ -410,7 +410,7 @@ def real_trees_block(ctx, peak):
                 "compact_frac": alg / 1e9 / (cm / 1e3) / peak, "whole_pass_frac": (alg + d["header_bytes"]) / 1e9 / ((pm + cm) / 1e3) / peak,
                 "kernels_gbs_input": in_bytes / 1e9 / ((pm + cm) / 1e3),
                 "tree_s": min(tt), "tree_first_call_s": tt[0], "tree_gbs": in_bytes / 1e9 / min(tt),
-                "tree_phases_s": {k: st[k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s")},
+                "tree_phases_s": {k: st[k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s", "read_cpu_s", "write_cpu_s", "dma_wait_s", "io_threads", "n_batches")},
                 "tree_identical_to_reference": bool(same),
                 "reference_serial_s": min(ser), "reference_serial_gbs": in_bytes / 1e9 / min(ser),
                 "reference_parallel_s": min(par), "reference_parallel_gbs": in_bytes / 1e9 / min(par), "cores": nproc,
@@ -698,7 +698,7 @@ def host_legs(a, ctx, corpus, batch, ns, peak):
         best = min(range(len(tt)), key=lambda k: tt[k])
         out["tree"] = {"value": n_bytes / 1e9 / tt[best], "unit": "GB/s", "s": tt[best], "first_call_s": tt[0], "runs_s": tt,
                        "files": ns, "in_gb": n_bytes / 1e9, "fallback_files": int(sts[best]["n_fallback"]), "failed_files": int(sts[best]["n_failed"]),
-                       "phases_s": {k: sts[best][k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s")},
+                       "phases_s": {k: sts[best][k] for k in ("walk_read_s", "gpu_s", "write_s", "fallback_s", "read_cpu_s", "write_cpu_s", "dma_wait_s", "io_threads", "n_batches")},
                        "identical_to_reference_tree": bool(same),
                        "vs_reference_parallel": (n_bytes / 1e9 / tt[best]) / r["parallel_gbs"], "vs_reference_serial": (n_bytes / 1e9 / tt[best]) / r["serial_gbs"],
                        "api": "lb2_strip_tree (the call that replaces project_build.py:260) on a fresh /dev/shm copy of the tree the reference line strips"}

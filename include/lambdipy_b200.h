@@ -98,6 +98,10 @@ typedef struct lb2_tree_stats {
   double gpu_s;               /* kernels + result fetch, summed over batches                    */
   double write_s;             /* file reads/uploads and downloads/writes (overlapped), wall     */
   double fallback_s;          /* host `strip` on the files the planner refused                  */
+  double read_cpu_s;          /* summed over the I/O threads: time inside pread                 */
+  double write_cpu_s;         /* ... inside pwrite / truncate                                   */
+  double dma_wait_s;          /* ... issuing and waiting for the slot DMAs                      */
+  uint32_t io_threads, n_batches;
   lb2_stats batch;
 } lb2_tree_stats;
 

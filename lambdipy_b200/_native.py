@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblambdipy_b200.so")
+LIB_PATH = os.environ.get("LAMBDIPY_B200_LIB") or os.path.join(_HERE, "liblambdipy_b200.so")  # (override: diagnostic builds)
 
 # return codes / status / flags (mirror include/lambdipy_b200.h)
 LB2_OK, LB2_E_CUDA, LB2_E_ARG, LB2_E_CAPACITY, LB2_E_IO, LB2_E_NODEVICE, LB2_E_STATE = 0, -1, -2, -3, -4, -5, -6
@@ -45,6 +45,7 @@ class TreeStats(C.Structure):
         ("n_failed", C.c_uint32), ("n_removed", C.c_uint32),
         ("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
         ("walk_read_s", C.c_double), ("gpu_s", C.c_double), ("write_s", C.c_double), ("fallback_s", C.c_double),
+        ("read_cpu_s", C.c_double), ("write_cpu_s", C.c_double), ("dma_wait_s", C.c_double), ("io_threads", C.c_uint32), ("n_batches", C.c_uint32),
         ("batch", Stats),
     ]
 

@@ -894,6 +894,8 @@ int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32
   std::condition_variable cv_work, cv_done;
   bool quit = false;
   std::atomic<int> io_fail{0};
+  std::atomic<uint64_t> ns_read{0}, ns_write{0}, ns_dma{0};  // summed over workers: where the I/O threads spend their time
+  auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   std::vector<std::atomic<int>> read_bad(n), write_bad(n);
   std::vector<std::atomic<uint32_t>> segs_left(n);
   for (uint32_t i = 0; i < n; i++) { read_bad[i] = 0; write_bad[i] = 0; segs_left[i] = 0; }
@@ -913,19 +915,27 @@ int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32
     cudaEvent_t ev = w.ev[w.k & 1];
     w.k++;
     if (sl.upload) {
+      uint64_t t0 = now_ns();
       cudaEventSynchronize(ev);  // the DMA that last read this slot has finished
+      uint64_t t1 = now_ns();
       for (uint32_t q = sl.seg0; q < sl.seg1; q++) {
         const Seg &sg = segs[q];
         int fd = open(files[sg.file].path.c_str(), O_RDONLY | O_CLOEXEC);
         if (fd < 0 || !pread_all(fd, slot + sg.slot_off, sg.len, sg.file_off)) { read_bad[sg.file]++; io_fail++; }
         if (fd >= 0) close(fd);
       }
+      uint64_t t2 = now_ns();
       cudaMemcpyAsync(sl.dev, slot, sl.len, cudaMemcpyHostToDevice, w.stream);
       cudaEventRecord(ev, w.stream);
+      ns_dma += (t1 - t0) + (now_ns() - t2); ns_read += t2 - t1;
     } else {
+      uint64_t t0 = now_ns();
       cudaMemcpyAsync(slot, sl.dev, sl.len, cudaMemcpyDeviceToHost, w.stream);
       cudaEventRecord(ev, w.stream);
       if (cudaEventSynchronize(ev) != cudaSuccess) io_fail++;
+      uint64_t t1 = now_ns();
+      ns_dma += t1 - t0;
+      const uint64_t tw0 = t1;
       for (uint32_t q = sl.seg0; q < sl.seg1; q++) {
         const Seg &sg = segs[q];
         // no O_TRUNC, no temp file: the bytes go into the pages the file already has (see walk())
@@ -934,6 +944,7 @@ int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32
         if (fd >= 0) close(fd);
         if (--segs_left[sg.file] == 0) finish_file(sg.file);
       }
+      ns_write += now_ns() - tw0;
     }
   };
   std::vector<std::thread> pool;
@@ -1099,6 +1110,8 @@ int lb2_strip_tree_ex(lb2_ctx *ctx, const char *root, const char *suffix, uint32
   cudaStreamSynchronize(ctx->stream);
   for (void *p : tmp_dev) cudaFree(p);
   st.gpu_s = t_gpu;
+  st.read_cpu_s = ns_read.load() * 1e-9; st.write_cpu_s = ns_write.load() * 1e-9; st.dma_wait_s = ns_dma.load() * 1e-9;
+  st.io_threads = (uint32_t)E.n_workers; st.n_batches = (uint32_t)batches.size();
   st.write_s = now_s() - t_io0 - t_gpu;  // read/upload and download/write overlap: I/O wall time next to the kernels
   if (rc) { if (st_out) *st_out = st; return rc; }
 

@@ -1,8 +1,21 @@
-// plan.cu -- the ELF "plan" kernel: one warp per file parses Ehdr / Shdr / Phdr / .shstrtab out of
-// the HBM input arena with coalesced 16-byte loads, decides keep/drop per section (warp ballot),
-// lays the stripped file out exactly as GNU strip (Binutils 2.42) would, regenerates .shstrtab,
-// the section-header table, the program-header table and merged build-attribute notes into a
-// per-file scratch slot, and emits the list of (src,dst,len) tiles the compaction kernel executes.
+// plan.cu -- the ELF "plan" kernel: one 128-thread CTA per file parses Ehdr / Shdr / Phdr / .shstrtab out
+// of the HBM input arena with coalesced 16-byte loads, decides keep/drop per section, lays the stripped
+// file out exactly as GNU strip (Binutils 2.42) would, regenerates .shstrtab, the section-header table,
+// the program-header table and merged build-attribute notes into a per-file scratch slot, and emits the
+// list of (src,dst,len) tiles the compaction kernel executes.
+//
+// The kernel is latency-bound (a few KB of headers per file, long dependent chains), so the work is
+// organised to shorten the critical path rather than to move bytes:
+//   * one thread per section header / program header for everything that is independent per entry
+//     (input gate, keep/drop, name hashes, segment membership, new headers);
+//   * after the section order is known, the three long independent jobs run on different warps at
+//     the same time:  warp 0 program headers + LOAD layout (R10-R12), warp 1 build-attribute note
+//     merging (R9), warp 2 the tail-merged .shstrtab (R6);
+//   * the sequential parts that remain (LOAD cursor, non-alloc packing, note range inheritance) touch a
+//     handful of values each; the note sorts -- glibc's merge sort restated level by level -- compare
+//     register-resident keys and prefetch the next element of both runs;
+//   * one launch for every file: the note workspace (320 notes) aliases the extent arrays, note bytes are
+//     read through L1 straight from the arena.
 //
 // Replaces, per file, what the reference delegates to the external `strip` binary:
 // /root/reference/lambdipy/project_build.py:260.  Rules R1..R12: /root/repo/SURVEY.md 8(c).
@@ -15,24 +28,32 @@
 
 namespace lb2 {
 
-struct DNote {
+constexpr int PLAN_THREADS = 128;
+
+// One build-attribute note.  16-byte halves: {start,end} and the packed rest, so a merge step loads
+// two vectors per element.
+struct __align__(16) DNote {
   uint64_t start, end;
-  uint64_t key;     // bytes 3..10 of the name, big-endian packed, zero padded: decides most name comparisons
-  uint32_t type;
-  uint16_t off;     // offset of the note header inside note_buf
+  uint16_t type;    // 0x100 OPEN, 0x101 FUNC, 0 deleted
+  uint16_t nrank;   // rank of the attribute name among the distinct names (valid when !names_ambiguous)
+  uint16_t off;     // offset of the note header inside the section
   uint16_t namesz;
   uint16_t cls;     // index of the first note with the identical name (equality class)
   uint8_t ver;      // is a "GA$<version>" note
   uint8_t pad;
+  uint32_t tag;     // name hash and length packed: one compare filters class candidates
 };
+static_assert(sizeof(DNote) == 32, "DNote is read as two 16-byte vectors");
 
-template <int NB, int NN> struct NoteSmem {
-  DNote notes[NN];
-  uint16_t perm[NN], tmp[NN];
-  uint32_t tag[NN];
-  __align__(16) uint8_t buf[NB];
+struct NoteWork {
+  DNote notes[MAX_NOTES];
+  uint64_t key[MAX_NOTES];   // bytes 3..10 of the name, big-endian packed, zero padded: decides most name comparisons
+  uint16_t perm[MAX_NOTES], tmp[MAX_NOTES];
 };
-constexpr int32_t ST_RETRY_BIG_NOTES = 100;  // internal: small-variant verdict, never leaves the device
+struct ExtWork {
+  uint64_t src[MAX_EXT], dst[MAX_EXT], len[MAX_EXT];
+  uint32_t tiles[MAX_EXT];
+};
 
 struct PlanSmem {
   Ehdr eh;
@@ -42,40 +63,40 @@ struct PlanSmem {
   uint64_t new_off[MAX_SH];
   uint64_t new_size[MAX_SH];
   uint64_t src_addr[MAX_SH];  // absolute device address of the section's bytes (input or scratch)
-  uint64_t ext_src[MAX_EXT], ext_dst[MAX_EXT], ext_len[MAX_EXT];
-  uint32_t ext_tiles[MAX_EXT];
-  uint64_t ent_key[MAX_SH + 1];   // last 8 characters of each unique name, reversed (phase J)
+  uint64_t memb[MAX_PH];      // kept sections program header j carries (BFD ELF_SECTION_IN_SEGMENT)
+  uint64_t seg_mask[MAX_PH];  // kept alloc sections laid out with PT_LOAD j
+  uint64_t seg_bits[MAX_PH];  // ... of which have file contents (not NOBITS)
+  uint64_t load_rel_end[MAX_PH], load_mem_top[MAX_PH], load_newoff[MAX_PH], load_base[MAX_PH];
+  uint64_t ent_key[MAX_SH + 1];   // last 8 characters of each unique name, reversed
   uint32_t ent_off[MAX_SH + 1];
   uint16_t ent_str[MAX_SH + 1];
   uint16_t ent_len[MAX_SH + 1];
   int16_t ent_host[MAX_SH + 1];
   uint8_t ent_sorted[MAX_SH + 1];
+  uint8_t ent_pos[MAX_SH + 1];    // position of each entry in the sorted order
   uint8_t sec_ent[MAX_SH];
   int8_t seg[MAX_SH];
   uint8_t keep[MAX_SH];
   uint8_t new_index[MAX_SH];
   uint8_t order[MAX_SH + 1];
   uint8_t pkeep[MAX_PH];
-  uint8_t piece[MAX_SH];
-  uint16_t name_len[MAX_SH];     // strlen of each section's name          (lane-parallel, phase C)
+  uint8_t piece[MAX_SH + 1];
+  uint16_t name_len[MAX_SH];     // strlen of each section's name
   uint32_t name_hash[MAX_SH];    // FNV-1a of each section's name: cheap inequality test
-  uint64_t seg_mask[MAX_PH];     // kept sections carried by PT_LOAD j     (phase F)
-  uint64_t seg_bits[MAX_PH];     // ... of which have file contents (not NOBITS)
   char names[MAX_STR + 16];
-  // build-attribute note workspace: lives in a second shared array whose size is a template
-  // parameter of the kernel (small for the common case so that more files fit per SM; files with
-  // bigger note sections are redone by the large variant)
-  DNote *notes;
-  uint16_t *note_perm;
-  uint16_t *note_tmp;
-  uint8_t *note_buf;
-  uint32_t *note_tag;
-  int note_cap_bytes, note_cap_n;
-  // scalars shared by the warp
-  int fail;
-  int nk, nent, n_ext, new_phnum, note_tie;
+  // build-attribute note workspace (phase E, warp 1) and the extent list (phases L/M) are never live together
+  union { NoteWork n; ExtWork x; } u;
+  // scalars shared by the CTA
+  int fail, fail_e, err_mal, err_uns, need_hoist, names_ambiguous;
+  int nk, nent, n_ext, new_phnum;
+  uint32_t keep32[2], alloc32[2], nobits32[2];
   uint32_t strsz, new_strsz;
-  uint64_t cur, shstr_off, new_shoff, total, hdr_bytes;
+  uint64_t cur, shstr_off, new_shoff, total, hdr_bytes, note_hdr_bytes, copy_bytes;
+  unsigned long long tile_base;
+  uint32_t n_tiles;
+#ifdef LB2_PLAN_TIMING
+  long long t_warp[4];
+#endif
 };
 
 // ---------------------------------------------------------------- small device helpers
@@ -97,27 +118,6 @@ __device__ __forceinline__ uint32_t d_hash(const char *s, int *len_out) {
   for (; s[n]; n++) h = (h ^ (uint8_t)s[n]) * 16777619u;
   *len_out = n;
   return h;
-}
-
-// Warp-cooperative global->shared copy.  16-byte vector loads when both sides allow it (the
-// Shdr table of a BFD/ld/lld-written file sits at an 8- or 16-aligned e_shoff and every file
-// base in the arena is 16-aligned), 8-byte, then byte loads otherwise.
-__device__ __forceinline__ void warp_g2s(void *dst_s, const uint8_t *src_g, uint32_t nbytes, int lane) {
-  uintptr_t s = reinterpret_cast<uintptr_t>(src_g);
-  uint8_t *d = static_cast<uint8_t *>(dst_s);
-  if (((s | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
-    uint32_t nv = nbytes >> 4;
-    for (uint32_t i = lane; i < nv; i += 32)
-      reinterpret_cast<uint4 *>(d)[i] = __ldg(reinterpret_cast<const uint4 *>(src_g) + i);
-    for (uint32_t i = (nv << 4) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
-  } else if (((s | reinterpret_cast<uintptr_t>(d)) & 7) == 0) {
-    uint32_t nv = nbytes >> 3;
-    for (uint32_t i = lane; i < nv; i += 32)
-      reinterpret_cast<uint2 *>(d)[i] = __ldg(reinterpret_cast<const uint2 *>(src_g) + i);
-    for (uint32_t i = (nv << 3) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
-  } else {
-    for (uint32_t i = lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
-  }
 }
 
 // R1: BFD marks these non-alloc names SEC_DEBUGGING; strip removes them.
@@ -246,32 +246,44 @@ __device__ int strrev_cmp(const char *a, int la, const char *b, int lb) {
 }
 
 // ---------------------------------------------------------------- R9: objcopy merge_gnu_build_notes
-__device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
-  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#ifdef LB2_HOST_EMULATION
+#define LB2_PREFETCH_L1(p) do { } while (0)
+#else
+#define LB2_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#endif
+// note bytes are read straight from the arena (through L1); a hostile sh_offset may be unaligned
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) return __ldg(reinterpret_cast<const uint32_t *>(p));
+  return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
 }
-__device__ __forceinline__ uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
 __device__ __forceinline__ void wr32(uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; }
 __device__ __forceinline__ void wr64(uint8_t *p, uint64_t v) { wr32(p, (uint32_t)v); wr32(p + 4, (uint32_t)(v >> 32)); }
 
 // memcmp(name1 + 3, name2 + 3, min(namesz) - 3) of objcopy's compare_gnu_build_notes, answered from
-// the precomputed equality class and 8-byte key whenever they decide it
-__device__ __forceinline__ int cmp_note_names(const PlanSmem &sm, const DNote &a, const DNote &b) {
+// the equality class and the 8-byte key whenever they decide it
+__device__ __forceinline__ int cmp_note_names(const PlanSmem &sm, const uint8_t *nbuf, const DNote &a, uint64_t ka, const DNote &b, uint64_t kb) {
   if (a.cls == b.cls) return 0;
   const int m = (int)(a.namesz < b.namesz ? a.namesz : b.namesz) - 3;
   if (m <= 0) return 0;
   if (m >= 8) {
-    if (a.key != b.key) return a.key < b.key ? -1 : 1;
-    const uint8_t *n1 = sm.note_buf + a.off + 12 + 3, *n2 = sm.note_buf + b.off + 12 + 3;
-    for (int i = 8; i < m; i++) if (n1[i] != n2[i]) return (int)n1[i] - (int)n2[i];
+    if (ka != kb) return ka < kb ? -1 : 1;
+    const uint8_t *n1 = nbuf + a.off + 12 + 3, *n2 = nbuf + b.off + 12 + 3;
+    for (int i = 8; i < m; i++) { const int x = __ldg(n1 + i), y = __ldg(n2 + i); if (x != y) return x - y; }
     return 0;
   }
-  const uint64_t x = a.key >> (8 * (8 - m)), y = b.key >> (8 * (8 - m));
+  const uint64_t x = ka >> (8 * (8 - m)), y = kb >> (8 * (8 - m));
   return x == y ? 0 : (x < y ? -1 : 1);
 }
-// first sort: by attribute name, then by range (objcopy.c compare_gnu_build_notes)
-__device__ int cmp_by_attr(const PlanSmem &sm, const DNote &a, const DNote &b) {
-  const int c = cmp_note_names(sm, a, b);
-  if (c) return c;
+// first sort: by attribute name, then by range (objcopy.c compare_gnu_build_notes).  FAST: the names of
+// distinct classes are totally ordered (no name is a prefix of another), so their ranks decide.
+template <bool FAST>
+__device__ __forceinline__ int cmp_by_attr(const PlanSmem &sm, const uint8_t *nbuf, const DNote &a, uint16_t pa, const DNote &b, uint16_t pb) {
+  if (FAST) {
+    if (a.nrank != b.nrank) return a.nrank < b.nrank ? -1 : 1;
+  } else {
+    const int c = cmp_note_names(sm, nbuf, a, sm.u.n.key[pa], b, sm.u.n.key[pb]);
+    if (c) return c;
+  }
   if (a.end < b.start) return -1;
   if (a.start > b.end) return 1;
   if (a.start < b.start) return -1;
@@ -282,7 +294,7 @@ __device__ int cmp_by_attr(const PlanSmem &sm, const DNote &a, const DNote &b) {
   return 0;
 }
 // second sort: by address range (objcopy.c sort_gnu_build_notes)
-__device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
+__device__ __forceinline__ int cmp_by_addr(const DNote &a, const DNote &b) {
   if (a.type == 0x100 && b.type != 0x100) return -1;  // OPEN notes first
   if (a.type != 0x100 && b.type == 0x100) return 1;
   if (a.start < b.start) return -1;
@@ -298,7 +310,9 @@ __device__ int cmp_by_addr(const PlanSmem &sm, const DNote &a, const DNote &b) {
 // element while cmp(left, right) <= 0).  The recursion tree is restated level by level: at depth d the
 // segment of node k is found by halving [0, n) along the bits of k, all merges of one depth are
 // independent and run on different lanes, deepest level first -- the same comparisons in the same
-// order inside every merge as the recursive routine, 2n instead of n log n merge steps deep.
+// order inside every merge as the recursive routine, 2n instead of n log n merge steps deep.  Inside a
+// merge the heads of both runs live in registers and the element behind each head is already on its way
+// from shared memory while the heads are compared.
 __device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int *hi) {
   int l = 0, h = n;
   for (int b = depth - 1; b >= 0; b--) {
@@ -307,10 +321,11 @@ __device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int
   }
   *lo = l; *hi = h;
 }
-__device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
-  const DNote *__restrict__ notes = sm.notes;   // hoisted: PlanSmem only holds pointers to the note workspace
-  uint16_t *__restrict__ perm = sm.note_perm;
-  uint16_t *__restrict__ tmp = sm.note_tmp;
+template <bool SECOND, bool FAST>
+__device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int lane) {
+  const DNote *__restrict__ notes = sm.u.n.notes;
+  uint16_t *__restrict__ perm = sm.u.n.perm;
+  uint16_t *__restrict__ tmp = sm.u.n.tmp;
   int depth = 0;
   while ((1 << depth) < n) depth++;
   for (int d = depth - 1; d >= 0; d--) {
@@ -320,19 +335,22 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
       const int n1 = (hi - lo) / 2;
       int i = lo, j = lo + n1, w = lo, r1 = n1, r2 = (hi - lo) - n1;
       if (r1 == 0 || r2 == 0) continue;
-      // the heads of both runs live in registers; only the side that advanced is reloaded
       uint16_t pa = perm[i], pb = perm[j];
+      uint16_t pa_n = r1 > 1 ? perm[i + 1] : pa, pb_n = r2 > 1 ? perm[j + 1] : pb;
       DNote a = notes[pa], b = notes[pb];
+      DNote a_n = notes[pa_n], b_n = notes[pb_n];
       while (true) {
-        const int c = second ? cmp_by_addr(sm, a, b) : cmp_by_attr(sm, a, b);
+        const int c = SECOND ? cmp_by_addr(a, b) : cmp_by_attr<FAST>(sm, nbuf, a, pa, b, pb);
         if (c <= 0) {
           tmp[w++] = pa; i++;
           if (--r1 == 0) break;
-          pa = perm[i]; a = notes[pa];
+          pa = pa_n; a = a_n;
+          if (r1 > 1) { pa_n = perm[i + 1]; a_n = notes[pa_n]; }
         } else {
           tmp[w++] = pb; j++;
           if (--r2 == 0) break;
-          pb = perm[j]; b = notes[pb];
+          pb = pb_n; b = b_n;
+          if (r2 > 1) { pb_n = perm[j + 1]; b_n = notes[pb_n]; }
         }
       }
       while (r1 > 0) { tmp[w++] = perm[i++]; r1--; }
@@ -342,92 +360,98 @@ __device__ void warp_msort_notes(PlanSmem &sm, int n, bool second, int lane) {
   }
 }
 
-// Merges the notes held in sm.note_buf[0..size) and writes the result to `out` (global scratch).
-// Returns the new size; *err != 0 when objcopy would report corrupt notes.  Warp-collective.
+// 64-bit value of the nearest lane at or below `lane` whose bit is set in `mask`, else `carry`
+__device__ __forceinline__ uint64_t last_set_value(unsigned mask, uint64_t v, uint64_t carry, int lane) {
+  const unsigned m = mask & (0xffffffffu >> (31 - lane));
+  const int src = m ? 31 - __clz((int)m) : lane;
+  const uint64_t got = __shfl_sync(0xffffffffu, v, src);
+  return m ? got : carry;
+}
+
 #ifdef LB2_PLAN_TIMING
 #define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
 #else
 #define LB2_NT(k) do { } while (0)
 #endif
-__device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out, int *err, int lane) {
-  __shared__ int s_n, s_err;
-  __shared__ uint32_t s_newsize;
-  DNote *__restrict__ notes = sm.notes;          // hoisted out of shared memory once
-  uint16_t *__restrict__ perm = sm.note_perm;
-  uint16_t *__restrict__ tmp = sm.note_tmp;
-  const uint8_t *__restrict__ nbuf = sm.note_buf;
-  uint32_t *__restrict__ ntag = sm.note_tag;
-  const int note_cap = sm.note_cap_n;
+// Merges the `size` bytes of notes at nbuf (arena) and writes the result to `out` (global scratch).
+// Returns the new size; *err: 1 = objcopy would report corrupt notes, 2 = more notes than the workspace
+// holds.  Warp-collective (one warp).
+__device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_t size, uint8_t *out, int *err, int lane) {
+  DNote *__restrict__ notes = sm.u.n.notes;
+  uint16_t *__restrict__ perm = sm.u.n.perm;
+  uint16_t *__restrict__ tmp = sm.u.n.tmp;
+  uint64_t *__restrict__ nkey = sm.u.n.key;
 #ifdef LB2_PLAN_TIMING
-  long long nt_[8];
+  long long nt_[10];
 #endif
   LB2_NT(0);
+  for (uint32_t i = (uint32_t)lane * 128; i < size; i += 32 * 128) LB2_PREFETCH_L1(nbuf + i);
   // 1. lane 0 walks the variable-length records (three words each) and records where every note starts
+  int n = 0, e1 = 0;
   if (lane == 0) {
-    s_err = 0; s_n = 0;
-    int n = 0;
     uint32_t remain = size, p = 0;
     while (remain >= 12) {
-      if (n >= note_cap) { s_err = 2; break; }
-      const uint32_t *hw = reinterpret_cast<const uint32_t *>(nbuf + p);  // p stays a multiple of 4
-      const uint32_t namesz = hw[0], descsz = hw[1];
+      if (n >= MAX_NOTES) { e1 = 2; break; }
+      const uint32_t namesz = ldg32(nbuf + p), descsz = ldg32(nbuf + p + 4);
       const uint64_t padded = ((uint64_t)namesz + 3) & ~3ull;   // 64-bit: namesz = 0xffffffff must not wrap to 0
-      if (((descsz + 3) & ~3u) != descsz) { s_err = 1; break; }
-      if (padded + descsz + 12 > remain) { s_err = 1; break; }
+      if (((descsz + 3) & ~3u) != descsz) { e1 = 1; break; }
+      if (padded + descsz + 12 > remain) { e1 = 1; break; }
       notes[n].off = (uint16_t)p;
       perm[n] = (uint16_t)n;
       remain -= 12 + padded + descsz;
       p += 12 + padded + descsz;
       n++;
     }
-    if (!s_err && remain != 0) s_err = 1;
-    s_n = n;
+    if (!e1 && remain != 0) e1 = 1;
   }
+  n = __shfl_sync(0xffffffffu, n, 0);
+  e1 = __shfl_sync(0xffffffffu, e1, 0);
   __syncwarp();
-  if (s_err) { *err = s_err; return size; }
-  const int n = s_n;
+  if (e1) { *err = e1; return size; }
   // 2. every lane decodes its notes: checks, raw range, version class, comparison key and name hash
   {
     int bad = 0, v1 = 0, v2 = 0, v3 = 0;
     for (int i = lane; i < n; i += 32) {
       DNote &d = notes[i];
       const uint8_t *h = nbuf + d.off;
-      const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);
-      const uint32_t namesz = hw[0], descsz = hw[1], type = hw[2];
+      const uint32_t namesz = ldg32(h), descsz = ldg32(h + 4), type = ldg32(h + 8);
       const uint32_t padded = (namesz + 3) & ~3u;
       if (type != 0x100 && type != 0x101) { bad = 1; continue; }
       if (namesz < 3) { bad = 1; continue; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
       const uint8_t *nm = h + 12;
-      const uint32_t *dw = reinterpret_cast<const uint32_t *>(h + 12 + padded);
+      const uint8_t *dw = h + 12 + padded;
       d.namesz = (uint16_t)namesz;
-      d.type = type;
-      d.ver = 0;
-      if (nm[0] == '$' && nm[1] == 1 && nm[2] == '1') v1 = 1;
-      else if (namesz > 4 && nm[0] == 'G' && nm[1] == 'A' && nm[2] == '$' && nm[3] == 1) {
+      d.type = (uint16_t)type;
+      d.ver = 0; d.pad = 0; d.nrank = 0;
+      const uint8_t c0 = __ldg(nm), c1 = __ldg(nm + 1), c2 = __ldg(nm + 2);
+      if (c0 == '$' && c1 == 1 && c2 == '1') v1 = 1;
+      else if (namesz > 4 && c0 == 'G' && c1 == 'A' && c2 == '$' && __ldg(nm + 3) == 1) {
         d.ver = 1;
-        if (nm[4] == '2') v2 = 1;
-        else if (nm[4] == '3') v3 = 1;
+        const uint8_t c4 = __ldg(nm + 4);
+        if (c4 == '2') v2 = 1;
+        else if (c4 == '3') v3 = 1;
         else { bad = 1; continue; }
       }
       uint64_t start, end;
       if (descsz == 0) start = end = 0;
-      else if (descsz == 4) { start = dw[0]; end = ~0ull; }
-      else if (descsz == 8) { start = dw[0]; end = dw[1]; }
-      else if (descsz == 16) { start = (uint64_t)dw[0] | ((uint64_t)dw[1] << 32); end = (uint64_t)dw[2] | ((uint64_t)dw[3] << 32); }
+      else if (descsz == 4) { start = ldg32(dw); end = ~0ull; }
+      else if (descsz == 8) { start = ldg32(dw); end = ldg32(dw + 4); }
+      else if (descsz == 16) { start = (uint64_t)ldg32(dw) | ((uint64_t)ldg32(dw + 4) << 32); end = (uint64_t)ldg32(dw + 8) | ((uint64_t)ldg32(dw + 12) << 32); }
       else { bad = 1; continue; }
       if (start > end) start = end;
       d.start = start;   // raw; ranges inherited from earlier notes are filled in by step 3
       d.end = end;
-      if (nm[namesz - 1] != 0) { bad = 1; continue; }
+      if (__ldg(nm + namesz - 1) != 0) { bad = 1; continue; }
       uint64_t key = 0;
       uint32_t hsh = 2166136261u;
       for (int q = 0; q < (int)namesz; q++) {
-        hsh = (hsh ^ nm[q]) * 16777619u;
-        if (q >= 3 && q < 11) key = (key << 8) | nm[q];
+        const uint8_t ch = __ldg(nm + q);
+        hsh = (hsh ^ ch) * 16777619u;
+        if (q >= 3 && q < 11) key = (key << 8) | ch;
       }
       if (namesz <= 3) key = 0; else if (namesz < 11) key <<= 8 * (11 - namesz);
-      d.key = key;
-      ntag[i] = (hsh << 10) ^ namesz;  // name hash and length packed: one compare filters class candidates
+      nkey[i] = key;
+      d.tag = (hsh << 10) ^ namesz;
     }
     const unsigned mb = __ballot_sync(0xffffffffu, bad), m1 = __ballot_sync(0xffffffffu, v1), m2 = __ballot_sync(0xffffffffu, v2),
                    m3 = __ballot_sync(0xffffffffu, v3);
@@ -436,26 +460,29 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     if (!a1 && !a2 && !a3) a3 = true;  // "version note missing - assuming version 3"
     if ((a1 && a2) || (a1 && a3) || (a2 && a3)) { *err = 1; return size; }
     if (!a3 || size < 12) {            // only v3 notes are merged
-      for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
+      for (uint32_t i = lane; i < size; i += 32) out[i] = __ldg(nbuf + i);
       return size;
     }
   }
+  __syncwarp();
   LB2_NT(1);
-  // 3. a note without a range inherits the previous OPEN / FUNC note's: inherently sequential, two words per note
-  if (lane == 0) {
-    uint64_t pfs = 0, pos = 0, pfe = 0, poe = 0;
-    for (int i = 0; i < n; i++) {
-      DNote &d = notes[i];
-      const uint64_t start = d.start, end = d.end;
-      if (d.type == 0x100) {
-        if (start) pos = start;
-        if (end) poe = end;
-        d.start = pos; d.end = poe;
-      } else {
-        if (start) pfs = start;
-        if (end) pfe = end;
-        d.start = pfs; d.end = pfe;
-      }
+  // 3. a note without a range inherits the previous OPEN / FUNC note's ("if (start) pos = start; start = pos"):
+  //    the nearest earlier note of the same kind with a non-zero raw value, found with ballots, 32 notes a round
+  {
+    uint64_t pos = 0, poe = 0, pfs = 0, pfe = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n;
+      uint64_t s = 0, e = 0;
+      bool open = false;
+      if (valid) { s = notes[i].start; e = notes[i].end; open = notes[i].type == 0x100; }
+      const unsigned m_os = __ballot_sync(0xffffffffu, valid && open && s != 0), m_oe = __ballot_sync(0xffffffffu, valid && open && e != 0);
+      const unsigned m_fs = __ballot_sync(0xffffffffu, valid && !open && s != 0), m_fe = __ballot_sync(0xffffffffu, valid && !open && e != 0);
+      const uint64_t os = last_set_value(m_os, s, pos, lane), oe = last_set_value(m_oe, e, poe, lane);
+      const uint64_t fs = last_set_value(m_fs, s, pfs, lane), fe = last_set_value(m_fe, e, pfe, lane);
+      if (valid) { notes[i].start = open ? os : fs; notes[i].end = open ? oe : fe; }
+      pos = __shfl_sync(0xffffffffu, os, 31); poe = __shfl_sync(0xffffffffu, oe, 31);
+      pfs = __shfl_sync(0xffffffffu, fs, 31); pfe = __shfl_sync(0xffffffffu, fe, 31);
     }
   }
   __syncwarp();
@@ -463,75 +490,121 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
   for (int i = lane; i < n; i += 32) {
     DNote &d = notes[i];
     const uint8_t *nm = nbuf + d.off + 12;
-    const uint32_t tag = ntag[i];
+    const uint32_t tag = d.tag;
     int cls = i;
     for (int j = 0; j < i; j++) {
-      if (ntag[j] != tag) continue;
+      if (notes[j].tag != tag) continue;
       const uint8_t *om = nbuf + notes[j].off + 12;
       bool same = true;
-      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
+      for (int q = 0; q < (int)d.namesz; q++) if (__ldg(om + q) != __ldg(nm + q)) { same = false; break; }
       if (same) { cls = j; break; }
     }
     d.cls = (uint16_t)cls;
   }
   __syncwarp();
+  // 4b. rank of every distinct name among the distinct names; if two distinct names compare equal (one is
+  //     a prefix of the other beyond byte 3) ranks cannot stand in for the comparator: slow path
+  int amb = 0;
+  for (int i = lane; i < n; i += 32) {
+    const DNote d = notes[i];
+    if (d.cls != i) continue;
+    const uint64_t ki = nkey[i];
+    int less = 0;
+    for (int j = 0; j < n; j++) {
+      if (j == i || notes[j].cls != j) continue;
+      const int c = cmp_note_names(sm, nbuf, notes[j], nkey[j], d, ki);
+      less += c < 0;
+      amb |= c == 0;
+    }
+    notes[i].nrank = (uint16_t)less;
+  }
+  amb = __ballot_sync(0xffffffffu, amb) != 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) if (notes[i].cls != i) notes[i].nrank = notes[notes[i].cls].nrank;
+  __syncwarp();
   LB2_NT(2);
-  warp_msort_notes(sm, n, false, lane);   // restated glibc merge sort, level by level across lanes
+  if (amb) warp_msort_notes<false, false>(sm, nbuf, n, lane);   // restated glibc merge sort, level by level across lanes
+  else warp_msort_notes<false, true>(sm, nbuf, n, lane);
   LB2_NT(3);
+  // 5. objcopy's merge pass: every note looks back over the SURVIVING notes of the same attribute (at most 17).
+  //    The survivors so far are kept as a stack in tmp[], so deleted notes cost nothing to skip.
   if (lane == 0) {
+    int nl = 0;
     for (int i = 0; i < n; i++) {
-      DNote &pn = notes[perm[i]];
+      const uint16_t pi = perm[i];
+      DNote pn = notes[pi];
       if (pn.type == 0) continue;
-      if (pn.start == pn.end) { pn.type = 0; continue; }
+      if (pn.start == pn.end) { notes[pi].type = 0; continue; }
       int iter = 0;
-      for (int b = i - 1; b >= 0; b--) {
-        DNote &back = notes[perm[b]];
-        if (back.type == 0) continue;
+      bool dead = false;
+      for (int b = nl - 1; b >= 0; b--) {
+        DNote &back = notes[tmp[b]];
+        const uint64_t bs = back.start, be = back.end;
         if (back.cls != pn.cls) break;  // a different attribute name ends the search
-        if (back.start == pn.start && back.end == pn.end) { pn.type = 0; break; }
-        if (pn.start >= back.start && pn.end <= back.end) { pn.type = 0; break; }
+        if (bs == pn.start && be == pn.end) { dead = true; break; }
+        if (pn.start >= bs && pn.end <= be) { dead = true; break; }
         bool merge;
-        if (back.end < pn.start) merge = (((back.end + 15) & ~15ull) < pn.start);
-        else merge = (back.end != pn.end);
+        if (be < pn.start) merge = (((be + 15) & ~15ull) < pn.start);
+        else merge = (be != pn.end);
         if (back.type != pn.type) merge = false;  // OPEN and FUNC notes are never combined
         if (merge) {
-          if (pn.start < back.start) back.start = pn.start;
-          if (pn.end > back.end) back.end = pn.end;
-          pn.type = 0;
+          if (pn.start < bs) back.start = pn.start;
+          if (pn.end > be) back.end = pn.end;
+          dead = true;
           break;
         }
         if (iter++ > 16) break;
       }
+      if (dead) notes[pi].type = 0;
+      else tmp[nl++] = pi;
     }
   }
   __syncwarp();
   LB2_NT(4);
-  warp_msort_notes(sm, n, true, lane);
+  warp_msort_notes<true, true>(sm, nbuf, n, lane);
   LB2_NT(5);
-  if (lane == 0) {
-    // output offsets and range elision (depends on the previous surviving note): serial and cheap
-    uint32_t w = 0;
+  // 6. output offsets and range elision: a surviving note drops its description when its range equals the
+  //    previous survivor's.  Ballot + shuffle scan, 32 sorted positions a round.
+  uint32_t newsize = 0;
+  {
     uint64_t ps = 0, pe = 0;
-    for (int i = 0; i < n; i++) {
-      const DNote &pn = notes[perm[i]];
-      if (pn.type == 0) { tmp[i] = 0xffff; continue; }
-      const bool elide = (pn.start == ps && pn.end == pe);
-      tmp[i] = (uint16_t)((w >> 2) | (elide ? 0x8000u : 0u));  // offsets are multiples of 4, < 64 KB
-      w += 12 + ((pn.namesz + 3u) & ~3u) + (elide ? 0u : 16u);
-      if (!elide) { ps = pn.start; pe = pn.end; }
+    uint32_t run = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      DNote pn;
+      pn.type = 0; pn.start = pn.end = 0; pn.namesz = 0;
+      if (i < n) pn = notes[perm[i]];
+      const bool surv = i < n && pn.type != 0;
+      const unsigned ms = __ballot_sync(0xffffffffu, surv);
+      // previous survivor strictly below this lane, else the carry from earlier rounds
+      const unsigned below = lane ? (ms & (0xffffffffu >> (32 - lane))) : 0u;
+      const int src = below ? 31 - __clz((int)below) : lane;
+      const uint64_t qs = __shfl_sync(0xffffffffu, pn.start, src), qe = __shfl_sync(0xffffffffu, pn.end, src);
+      const uint64_t prev_s = below ? qs : ps, prev_e = below ? qe : pe;
+      const bool elide = surv && pn.start == prev_s && pn.end == prev_e;
+      const uint32_t v = surv ? 12u + ((pn.namesz + 3u) & ~3u) + (elide ? 0u : 16u) : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (i < n) tmp[i] = surv ? (uint16_t)(((run + inc - v) >> 2) | (elide ? 0x8000u : 0u)) : (uint16_t)0xffff;  // offsets are multiples of 4, < 64 KB
+      run += __shfl_sync(0xffffffffu, inc, 31);
+      if (ms) {
+        const int last = 31 - __clz((int)ms);
+        ps = __shfl_sync(0xffffffffu, pn.start, last); pe = __shfl_sync(0xffffffffu, pn.end, last);
+      }
     }
-    s_newsize = w;
+    newsize = run;
   }
   __syncwarp();
-  if (s_newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
-    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
+  if (newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
+    for (uint32_t i = lane; i < size; i += 32) out[i] = __ldg(nbuf + i);
     __syncwarp();
     return size;
   }
   for (int i = lane; i < n; i += 32) {
     const uint16_t t = tmp[i];
     if (t == 0xffff) continue;
-    const DNote &pn = notes[perm[i]];
+    const DNote pn = notes[perm[i]];
     const bool elide = (t & 0x8000u) != 0;
     uint8_t *o = out + ((uint32_t)(t & 0x7fffu) << 2);
     const uint32_t padded = (pn.namesz + 3u) & ~3u;
@@ -539,54 +612,66 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, uint32_t size, uint8_t *out,
     wr32(o + 4, elide ? 0u : 16u);
     wr32(o + 8, pn.type);
     const uint8_t *nm = nbuf + pn.off + 12;
-    for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? nm[q] : 0;
+    for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? __ldg(nm + q) : 0;
     if (!elide) { wr64(o + 12 + padded, pn.start); wr64(o + 20 + padded, pn.end); }
   }
   __syncwarp();
   LB2_NT(6);
 #ifdef LB2_PLAN_TIMING
-  if (lane == 0 && blockIdx.x == 0) printf("  notes n=%d: parse=%lld aids=%lld sort1=%lld merge=%lld sort2=%lld out=%lld\n", n, nt_[1]-nt_[0], nt_[2]-nt_[1], nt_[3]-nt_[2], nt_[4]-nt_[3], nt_[5]-nt_[4], nt_[6]-nt_[5]);
+  if (lane == 0 && blockIdx.x == 0) printf("  notes n=%d amb=%d: parse=%lld aids=%lld sort1=%lld merge=%lld sort2=%lld out=%lld\n", n, amb, nt_[1]-nt_[0], nt_[2]-nt_[1], nt_[3]-nt_[2], nt_[4]-nt_[3], nt_[5]-nt_[4], nt_[6]-nt_[5]);
 #endif
-  return s_newsize;
+  return newsize;
 }
 
-#define LB2_FAIL(code) do { sm.fail = (code); } while (0)
 #ifdef LB2_PLAN_TIMING
-#define LB2_T(k) do { __syncwarp(); if (lane == 0) t_[k] = clock64(); } while (0)
+#define LB2_T(k) do { if (tid == 0) t_[k] = clock64(); } while (0)
 #else
 #define LB2_T(k) do { } while (0)
 #endif
 
-template <int NB, int NN, bool RETRY_PASS>
-__global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
+// CTA-cooperative global->shared copy.  16-byte vector loads when both sides allow it (the Shdr table of
+// a BFD/ld/lld-written file sits at an 8- or 16-aligned e_shoff and every file base in the arena is
+// 16-aligned), 8-byte, then byte loads otherwise.
+__device__ __forceinline__ void block_g2s(void *dst_s, const uint8_t *src_g, uint32_t nbytes, int tid) {
+  uintptr_t s = reinterpret_cast<uintptr_t>(src_g);
+  uint8_t *d = static_cast<uint8_t *>(dst_s);
+  if (((s | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    uint32_t nv = nbytes >> 4;
+    for (uint32_t i = tid; i < nv; i += PLAN_THREADS)
+      reinterpret_cast<uint4 *>(d)[i] = __ldg(reinterpret_cast<const uint4 *>(src_g) + i);
+    for (uint32_t i = (nv << 4) + tid; i < nbytes; i += PLAN_THREADS) d[i] = __ldg(src_g + i);
+  } else if (((s | reinterpret_cast<uintptr_t>(d)) & 7) == 0) {
+    uint32_t nv = nbytes >> 3;
+    for (uint32_t i = tid; i < nv; i += PLAN_THREADS)
+      reinterpret_cast<uint2 *>(d)[i] = __ldg(reinterpret_cast<const uint2 *>(src_g) + i);
+    for (uint32_t i = (nv << 3) + tid; i < nbytes; i += PLAN_THREADS) d[i] = __ldg(src_g + i);
+  } else {
+    for (uint32_t i = tid; i < nbytes; i += PLAN_THREADS) d[i] = __ldg(src_g + i);
+  }
+}
+
+#define LB2_REJECT(code) do { if (tid == 0) { a.status[f] = (code); a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; } while (0)
+
+__global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
   __shared__ PlanSmem sm;
-  __shared__ NoteSmem<NB, NN> ns;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t f = blockIdx.x;
   if (f >= a.n_files) return;
-  if (RETRY_PASS && a.status[f] != ST_RETRY_BIG_NOTES) return;
 #ifdef LB2_PLAN_TIMING
   long long t_[16];
   for (int q = 0; q < 16; q++) t_[q] = 0;
 #endif
   LB2_T(0);
-  if (lane == 0) {
-    sm.notes = ns.notes; sm.note_perm = ns.perm; sm.note_tmp = ns.tmp; sm.note_buf = ns.buf; sm.note_tag = ns.tag;
-    sm.note_cap_bytes = NB; sm.note_cap_n = NN;
-  }
   const uint64_t base = a.in_off[f];
   const uint64_t n = a.in_size[f];
   const uint8_t *in = a.in + base;
   uint8_t *scr = a.scratch + (uint64_t)f * SCR_STRIDE;
 
-  if (lane == 0) { sm.fail = 0; sm.note_tie = 0; }
-  __syncwarp();
-
-  LB2_T(1);
-  // ---- A. Ehdr
-  if (n < 64) { if (lane == 0) { a.status[f] = ST_NOT_ELF; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-  if (lane < 4) reinterpret_cast<uint4 *>(&sm.eh)[lane] = __ldg(reinterpret_cast<const uint4 *>(in) + lane);
-  __syncwarp();
+  // ---- A. Ehdr (every exit below is taken by the whole CTA: verdicts come from shared memory)
+  if (n < 64) LB2_REJECT(ST_NOT_ELF);
+  if (tid < 4) reinterpret_cast<uint4 *>(&sm.eh)[tid] = __ldg(reinterpret_cast<const uint4 *>(in) + tid);
+  if (tid == 0) { sm.fail = 0; sm.fail_e = 0; sm.err_mal = 0; sm.err_uns = 0; sm.need_hoist = 0; sm.names_ambiguous = 0; sm.note_hdr_bytes = 0; }
+  __syncthreads();
   const Ehdr &eh = sm.eh;
   int st = ST_OK;
   if (!(eh.e_ident[0] == 0x7f && eh.e_ident[1] == 'E' && eh.e_ident[2] == 'L' && eh.e_ident[3] == 'F')) st = ST_NOT_ELF;
@@ -602,153 +687,165 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
   else if (eh.e_shstrndx >= eh.e_shnum) st = ST_MALFORMED;
   else if (eh.e_phnum && eh.e_phoff != 64) st = ST_UNSUPPORTED_LAYOUT;
   else if (eh.e_shnum > MAX_SH || eh.e_phnum > MAX_PH) st = ST_PLANNER_LIMIT;
-  if (st != ST_OK) { if (lane == 0) { a.status[f] = st; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  if (st != ST_OK) LB2_REJECT(st);
   const int shnum = eh.e_shnum, phnum = eh.e_phnum;
 
-  LB2_T(2);
+  LB2_T(1);
   // ---- B. section headers, program headers, section names: coalesced vector loads into smem
-  warp_g2s(sm.sh, in + eh.e_shoff, (uint32_t)shnum * 64, lane);
-  if (phnum) warp_g2s(sm.ph, in + eh.e_phoff, (uint32_t)phnum * 56, lane);
-  __syncwarp();
+  block_g2s(sm.sh, in + eh.e_shoff, (uint32_t)shnum * 64, tid);
+  if (phnum) block_g2s(sm.ph, in + eh.e_phoff, (uint32_t)phnum * 56, tid);
+  __syncthreads();
   {
     const Shdr &strh = sm.sh[eh.e_shstrndx];
     if (strh.sh_type != SHT_STRTAB || strh.sh_offset > n || strh.sh_size > n - strh.sh_offset || strh.sh_size == 0) st = ST_MALFORMED;
     else if (strh.sh_size > MAX_STR) st = ST_PLANNER_LIMIT;
-    if (st != ST_OK) { if (lane == 0) { a.status[f] = st; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-    const uint32_t strsz = (uint32_t)strh.sh_size;
+    if (st != ST_OK) LB2_REJECT(st);
+    const uint32_t strsz0 = (uint32_t)strh.sh_size;
     // byte loads unless the table happens to be 16-aligned (it rarely is; it is <= 2 KB)
-    warp_g2s(sm.names, in + strh.sh_offset, strsz, lane);
-    if (lane < 10) sm.names[strsz + lane] = ".shstrtab"[lane];  // literal appended behind the table
-    if (lane == 0) { sm.strsz = strsz; sm.hdr_bytes = (uint64_t)shnum * 64 + strsz + (uint64_t)phnum * 56 + 64; }
-    __syncwarp();
-    if (sm.names[strsz - 1] != 0) { if (lane == 0) { a.status[f] = ST_MALFORMED; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+    block_g2s(sm.names, in + strh.sh_offset, strsz0, tid);
+    if (tid < 10) sm.names[strsz0 + tid] = ".shstrtab"[tid];  // literal appended behind the table
+    if (tid == 0) { sm.strsz = strsz0; sm.hdr_bytes = (uint64_t)shnum * 64 + strsz0 + (uint64_t)phnum * 56 + 64; }
   }
+  __syncthreads();
   const uint32_t strsz = sm.strsz;
+  if (sm.names[strsz - 1] != 0) LB2_REJECT(ST_MALFORMED);
+
+  LB2_T(2);
+  // ---- C. input gate + R1 keep/drop: thread i <-> section i (warps 0-1), thread 64+j <-> program header j (warp 2)
+  if (tid >= 64 && tid - 64 < phnum) {
+    const int j = tid - 64;
+    const Phdr &p = sm.ph[j];
+    int err_uns = 0;
+    if (p.p_paddr != p.p_vaddr) err_uns = 1;                                   // section LMAs come from p_paddr
+    if (p.p_align & (p.p_align - 1)) err_uns = 1;                              // BFD: "invalid alignment"
+    if (p.p_type == PT_LOAD) {
+      if (p.p_align > 1 && ((p.p_vaddr - p.p_offset) & (p.p_align - 1))) err_uns = 1;
+      if (p.p_filesz > p.p_memsz || p.p_vaddr + p.p_memsz < p.p_vaddr || p.p_offset + p.p_filesz < p.p_offset) err_uns = 1;
+      for (int l = 0; l < j; l++) {                                            // ascending, non-overlapping LOADs
+        const Phdr &o = sm.ph[l];
+        if (o.p_type != PT_LOAD) continue;
+        if (p.p_vaddr < o.p_vaddr + o.p_memsz) err_uns = 1;
+        if (p.p_filesz && o.p_filesz && p.p_offset < o.p_offset + o.p_filesz) err_uns = 1;
+      }
+    }
+    if (p.p_type == PT_PHDR && (p.p_offset != 64 || p.p_filesz != (uint64_t)phnum * 56 || p.p_memsz != (uint64_t)phnum * 56)) err_uns = 1;
+    if (p.p_type == PT_GNU_STACK && (p.p_offset || p.p_vaddr || p.p_filesz || p.p_memsz)) err_uns = 1;
+    if (err_uns) sm.err_uns = 1;
+  }
+  if (tid >= 96 && tid < 104 && reinterpret_cast<const uint64_t *>(&sm.sh[0])[tid - 96] != 0) sm.err_uns = 1;  // section 0: the all-zero NULL header
+  if (tid < 64) {
+    const int i = tid;
+    int is_keep = 0, is_alloc = 0, is_nobits = 0;
+    if (i < shnum) {
+      int err_mal = 0, err_uns = 0;
+      Shdr &h = sm.sh[i];
+      sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
+      sm.src_addr[i] = reinterpret_cast<uint64_t>(in) + h.sh_offset;
+      if (h.sh_name >= strsz) err_mal = 1;
+      else if (h.sh_type != SHT_NOBITS && h.sh_type != SHT_NULL && (h.sh_offset > n || h.sh_size > n - h.sh_offset)) err_mal = 1;
+      else {
+        { int ln; sm.name_hash[i] = d_hash(sm.names + h.sh_name, &ln); sm.name_len[i] = (uint16_t)ln; }
+        if (i == 0) is_keep = 1;
+        else {
+          const char *nm = sm.names + h.sh_name;
+          const bool alloc = (h.sh_flags & SHF_ALLOC) != 0;
+          bool drop = false;
+          if (h.sh_type == SHT_SYMTAB || h.sh_type == SHT_SYMTAB_SHNDX) drop = true;
+          else if (h.sh_type == SHT_STRTAB && !alloc) drop = true;
+          else if (!alloc && is_debug_name(nm)) drop = true;
+          if (h.sh_type == SHT_NULL || h.sh_type == SHT_GROUP) err_uns = 1;
+          if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
+          if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
+          if (h.sh_type == 19 /* SHT_RELR */ && h.sh_entsize != 8) err_uns = 1;
+          if (h.sh_type == SHT_REL && h.sh_entsize != 16) err_uns = 1;
+          if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
+          {  // ---- gate (see expected_type_by_name)
+            const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;
+            const int want = expected_type_by_name(nm);
+            if (h.sh_flags & ~ALLOWED) err_uns = 1;
+            if (!type_is_known(h.sh_type)) err_uns = 1;
+            if (h.sh_type == SHT_NOBITS && !alloc) err_uns = 1;
+            if (want >= 0 && (uint32_t)want != h.sh_type && !(h.sh_type == 0x70000001u && want == (int)SHT_PROGBITS)) err_uns = 1;
+            if ((h.sh_flags & SHF_INFO_LINK) && h.sh_type != SHT_RELA && h.sh_type != SHT_REL) err_uns = 1;
+            if (h.sh_link >= (uint32_t)shnum) err_uns = 1;
+            else {
+              const Shdr &lk = sm.sh[h.sh_link];
+              const char *lname = lk.sh_name < strsz ? sm.names + lk.sh_name : "";
+              switch (h.sh_type) {
+                case SHT_DYNSYM: case SHT_DYNAMIC: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED:  // BFD: sh_link := index of .dynstr
+                  if (h.sh_link == 0 || !d_streq(lname, ".dynstr")) err_uns = 1;
+                  if (h.sh_type == SHT_DYNAMIC && h.sh_info != 0) err_uns = 1;
+                  if (h.sh_type == SHT_DYNSYM && (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24)) err_uns = 1;
+                  break;
+                case SHT_HASH: case SHT_GNU_HASH: case SHT_GNU_VERSYM:                         // BFD: sh_link := index of .dynsym
+                  if (h.sh_link == 0 || !d_streq(lname, ".dynsym") || h.sh_info != 0) err_uns = 1;
+                  break;
+                case SHT_RELA: case SHT_REL:
+                  if (h.sh_link != 0 && !d_streq(lname, ".dynsym")) err_uns = 1;
+                  if (h.sh_info >= (uint32_t)shnum) err_uns = 1;
+                  break;
+                case SHT_SYMTAB:  // dropped, but BFD reads it first and refuses a broken one
+                  if (h.sh_link == 0 || lk.sh_type != SHT_STRTAB || (lk.sh_flags & SHF_ALLOC)) err_uns = 1;
+                  if (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24) err_uns = 1;
+                  break;
+                default:          // ordinary sections (and string tables): BFD writes sh_link = sh_info = 0
+                  if (h.sh_link != 0 || h.sh_info != 0) err_uns = 1;
+                  break;
+              }
+            }
+          }
+          is_keep = drop ? 0 : 1;
+          is_alloc = alloc;
+          is_nobits = h.sh_type == SHT_NOBITS;
+        }
+      }
+      if (err_mal) sm.err_mal = 1;
+      if (err_uns) sm.err_uns = 1;
+      sm.keep[i] = (uint8_t)is_keep;
+    }
+    // the three masks every later phase works from: kept, kept+alloc, kept+NOBITS
+    const unsigned mk = __ballot_sync(0xffffffffu, is_keep), ma = __ballot_sync(0xffffffffu, is_keep && is_alloc),
+                   mn = __ballot_sync(0xffffffffu, is_keep && is_nobits);
+    if (lane == 0) { sm.keep32[warp] = mk; sm.alloc32[warp] = ma; sm.nobits32[warp] = mn; }
+  }
+  __syncthreads();
+  if (sm.err_mal || sm.err_uns) LB2_REJECT(sm.err_mal ? ST_MALFORMED : ST_UNSUPPORTED_LAYOUT);
+  const uint64_t keepmask = (uint64_t)sm.keep32[0] | ((uint64_t)sm.keep32[1] << 32);
+  const uint64_t allocmask = (uint64_t)sm.alloc32[0] | ((uint64_t)sm.alloc32[1] << 32);
+  const uint64_t nobitsmask = (uint64_t)sm.nobits32[0] | ((uint64_t)sm.nobits32[1] << 32);
 
   LB2_T(3);
-  // ---- C. R1 keep/drop mask, lane i <-> sections i and i+32; verdicts combined by ballot
-  {
-    int err_mal = 0, err_uns = 0;
-    if (lane < phnum) {  // gate on the program headers (one per lane)
-      const Phdr &p = sm.ph[lane];
-      if (p.p_paddr != p.p_vaddr) err_uns = 1;                                   // section LMAs come from p_paddr
-      if (p.p_align & (p.p_align - 1)) err_uns = 1;                              // BFD: "invalid alignment"
-      if (p.p_type == PT_LOAD) {
-        if (p.p_align > 1 && ((p.p_vaddr - p.p_offset) & (p.p_align - 1))) err_uns = 1;
-        if (p.p_filesz > p.p_memsz || p.p_vaddr + p.p_memsz < p.p_vaddr || p.p_offset + p.p_filesz < p.p_offset) err_uns = 1;
-        for (int l = 0; l < lane; l++) {                                          // ascending, non-overlapping LOADs
-          const Phdr &o = sm.ph[l];
-          if (o.p_type != PT_LOAD) continue;
-          if (p.p_vaddr < o.p_vaddr + o.p_memsz) err_uns = 1;
-          if (p.p_filesz && o.p_filesz && p.p_offset < o.p_offset + o.p_filesz) err_uns = 1;
-        }
-      }
-      if (p.p_type == PT_PHDR && (p.p_offset != 64 || p.p_filesz != (uint64_t)phnum * 56 || p.p_memsz != (uint64_t)phnum * 56)) err_uns = 1;
-      if (p.p_type == PT_GNU_STACK && (p.p_offset || p.p_vaddr || p.p_filesz || p.p_memsz)) err_uns = 1;
-    }
-    if (lane < 8 && reinterpret_cast<const uint64_t *>(&sm.sh[0])[lane] != 0) err_uns = 1;  // section 0: the all-zero NULL header
-    for (int i = lane; i < shnum; i += 32) {
-      Shdr &h = sm.sh[i];
-      sm.keep[i] = 0; sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
-      sm.src_addr[i] = reinterpret_cast<uint64_t>(in) + h.sh_offset;
-      if (h.sh_name >= strsz) { err_mal = 1; continue; }
-      if (h.sh_type != SHT_NOBITS && h.sh_type != SHT_NULL && (h.sh_offset > n || h.sh_size > n - h.sh_offset)) { err_mal = 1; continue; }
-      { int ln; sm.name_hash[i] = d_hash(sm.names + h.sh_name, &ln); sm.name_len[i] = (uint16_t)ln; }
-      if (i == 0) { sm.keep[0] = 1; continue; }
-      const char *nm = sm.names + h.sh_name;
-      const bool alloc = (h.sh_flags & SHF_ALLOC) != 0;
-      bool drop = false;
-      if (h.sh_type == SHT_SYMTAB || h.sh_type == SHT_SYMTAB_SHNDX) drop = true;
-      else if (h.sh_type == SHT_STRTAB && !alloc) drop = true;
-      else if (!alloc && is_debug_name(nm)) drop = true;
-      if (h.sh_type == SHT_NULL || h.sh_type == SHT_GROUP) err_uns = 1;
-      if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
-      if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
-      if (h.sh_type == 19 /* SHT_RELR */ && h.sh_entsize != 8) err_uns = 1;
-      if (h.sh_type == SHT_REL && h.sh_entsize != 16) err_uns = 1;
-      if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
-      {  // ---- gate (see expected_type_by_name)
-        const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;
-        const int want = expected_type_by_name(nm);
-        if (h.sh_flags & ~ALLOWED) err_uns = 1;
-        if (!type_is_known(h.sh_type)) err_uns = 1;
-        if (h.sh_type == SHT_NOBITS && !alloc) err_uns = 1;
-        if (want >= 0 && (uint32_t)want != h.sh_type && !(h.sh_type == 0x70000001u && want == (int)SHT_PROGBITS)) err_uns = 1;
-        if ((h.sh_flags & SHF_INFO_LINK) && h.sh_type != SHT_RELA && h.sh_type != SHT_REL) err_uns = 1;
-        if (h.sh_link >= (uint32_t)shnum) err_uns = 1;
-        else {
-          const Shdr &lk = sm.sh[h.sh_link];
-          const char *lname = lk.sh_name < strsz ? sm.names + lk.sh_name : "";
-          switch (h.sh_type) {
-            case SHT_DYNSYM: case SHT_DYNAMIC: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED:  // BFD: sh_link := index of .dynstr
-              if (h.sh_link == 0 || !d_streq(lname, ".dynstr")) err_uns = 1;
-              if (h.sh_type == SHT_DYNAMIC && h.sh_info != 0) err_uns = 1;
-              if (h.sh_type == SHT_DYNSYM && (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24)) err_uns = 1;
-              break;
-            case SHT_HASH: case SHT_GNU_HASH: case SHT_GNU_VERSYM:                         // BFD: sh_link := index of .dynsym
-              if (h.sh_link == 0 || !d_streq(lname, ".dynsym") || h.sh_info != 0) err_uns = 1;
-              break;
-            case SHT_RELA: case SHT_REL:
-              if (h.sh_link != 0 && !d_streq(lname, ".dynsym")) err_uns = 1;
-              if (h.sh_info >= (uint32_t)shnum) err_uns = 1;
-              break;
-            case SHT_SYMTAB:  // dropped, but BFD reads it first and refuses a broken one
-              if (h.sh_link == 0 || lk.sh_type != SHT_STRTAB || (lk.sh_flags & SHF_ALLOC)) err_uns = 1;
-              if (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24) err_uns = 1;
-              break;
-            default:          // ordinary sections (and string tables): BFD writes sh_link = sh_info = 0
-              if (h.sh_link != 0 || h.sh_info != 0) err_uns = 1;
-              break;
-          }
-        }
-      }
-      sm.keep[i] = drop ? 0 : 1;
-      // BFD keeps a power-of-two alignment the address honours: min(lowbit(align), lowbit(addr))
-      uint64_t al = h.sh_addralign ? lowbit(h.sh_addralign) : 1;
-      if (h.sh_addr) { uint64_t lb = lowbit(h.sh_addr); if (lb < al) al = lb; }
-      h.sh_addralign = al;
-    }
-    unsigned mal = __ballot_sync(0xffffffffu, err_mal), uns = __ballot_sync(0xffffffffu, err_uns);
-    if (mal || uns) { if (lane == 0) { a.status[f] = mal ? ST_MALFORMED : ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
+  // ---- D. R2 output order (a later dynsym is hoisted in front of the first REL/RELA that uses it) and
+  //         new section indices.  Also here, while every thread has its header at hand: BFD keeps a
+  //         power-of-two alignment the address honours, min(lowbit(align), lowbit(addr)).
+  if (tid < shnum && tid > 0) {
+    Shdr &h = sm.sh[tid];
+    if (((keepmask >> tid) & 1) && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && h.sh_link < (uint32_t)shnum && (int)h.sh_link > tid &&
+        ((keepmask >> h.sh_link) & 1) && (sm.sh[h.sh_link].sh_type == SHT_DYNSYM || sm.sh[h.sh_link].sh_type == SHT_SYMTAB))
+      sm.need_hoist = 1;
   }
-  __syncwarp();
-
-  LB2_T(4);
-  // ---- D. R2 output order (hoist of a later dynsym in front of the first section linking to
-  //         it ... BFD: in front of the first REL/RELA that uses it) and new section indices.
-  // Common case (no hoist, every linker-native file): new index = rank among the kept sections, straight
-  // from the ballot masks.  Only files that need the hoist take the serial walk.
-  bool need_hoist;
-  uint64_t keepmask;
-  {
-    int hoist = 0;
-    for (int i = lane; i < shnum; i += 32) {
-      const Shdr &h = sm.sh[i];
-      if (sm.keep[i] && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && h.sh_link < (uint32_t)shnum && (int)h.sh_link > i &&
-          sm.keep[h.sh_link] && (sm.sh[h.sh_link].sh_type == SHT_DYNSYM || sm.sh[h.sh_link].sh_type == SHT_SYMTAB))
-        hoist = 1;
-    }
-    need_hoist = __ballot_sync(0xffffffffu, hoist) != 0;
-    const unsigned lo = __ballot_sync(0xffffffffu, lane < shnum && sm.keep[lane]);
-    const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < shnum && sm.keep[lane + 32]);
-    keepmask = (uint64_t)lo | ((uint64_t)hi << 32);
+  __syncthreads();
+  if (tid < shnum && tid > 0) {
+    Shdr &h = sm.sh[tid];
+    uint64_t al = h.sh_addralign ? lowbit(h.sh_addralign) : 1;
+    if (h.sh_addr) { uint64_t lb = lowbit(h.sh_addr); if (lb < al) al = lb; }
+    h.sh_addralign = al;
   }
-  if (!need_hoist) {
-    for (int i = lane; i < shnum; i += 32)
-      if ((keepmask >> i) & 1) {
-        const int k = __popcll(keepmask & ((1ull << i) - 1));
-        sm.new_index[i] = (uint8_t)k;
-        sm.order[k] = (uint8_t)i;
-      }
-    if (lane == 0) sm.nk = __popcll(keepmask);
-  } else if (lane == 0) {
+  if (!sm.need_hoist) {
+    if (tid < shnum && ((keepmask >> tid) & 1)) {
+      const int k = __popcll(keepmask & ((1ull << tid) - 1));
+      sm.new_index[tid] = (uint8_t)k;
+      sm.order[k] = (uint8_t)tid;
+    }
+    if (tid == 0) sm.nk = __popcll(keepmask);
+  } else if (tid == 0) {
     uint64_t emitted = 0;
     int nk = 0;
     for (int i = 0; i < shnum; i++) {
-      if (!sm.keep[i] || ((emitted >> i) & 1)) continue;
+      if (!((keepmask >> i) & 1) || ((emitted >> i) & 1)) continue;
       const Shdr &h = sm.sh[i];
       if ((h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && h.sh_link < (uint32_t)shnum && (int)h.sh_link > i &&
-          sm.keep[h.sh_link] && !((emitted >> h.sh_link) & 1) &&
+          ((keepmask >> h.sh_link) & 1) && !((emitted >> h.sh_link) & 1) &&
           (sm.sh[h.sh_link].sh_type == SHT_DYNSYM || sm.sh[h.sh_link].sh_type == SHT_SYMTAB)) {
         sm.order[nk++] = (uint8_t)h.sh_link;
         emitted |= 1ull << h.sh_link;
@@ -759,368 +856,422 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     for (int k = 0; k < nk; k++) sm.new_index[sm.order[k]] = (uint8_t)k;
     sm.nk = nk;
   }
-  __syncwarp();
+  // ---- F1. which kept sections each program header carries: one header per warp-iteration, two ballots
+  for (int j = warp; j < phnum; j += PLAN_THREADS / 32) {
+    const Phdr &p = sm.ph[j];
+    const bool in0 = lane >= 1 && lane < shnum && ((keepmask >> lane) & 1) && sec_in_seg(sm.sh[lane], p);
+    const bool in1 = lane + 32 < shnum && ((keepmask >> (lane + 32)) & 1) && sec_in_seg(sm.sh[lane + 32], p);
+    const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+    if (lane == 0) sm.memb[j] = (uint64_t)m0 | ((uint64_t)m1 << 32);
+  }
+  __syncthreads();
   const int nk = sm.nk;
 
-  LB2_T(5);
-  // ---- E. R9 build-attribute note merging (sizes feed the layout)
-  if (!(a.flags & 1u)) {
-    uint32_t scr_used = 0;
-    for (int i = 1; i < shnum; i++) {
-      const Shdr &h = sm.sh[i];
-      if (!sm.keep[i] || h.sh_type != SHT_NOTE || (h.sh_flags & SHF_ALLOC)) continue;
-      if (!d_prefix(sm.names + h.sh_name, ".gnu.build.attributes")) continue;
-      if (h.sh_size > (uint64_t)NB || scr_used + h.sh_size > MAX_NOTE_BYTES) {
-        if (lane == 0) LB2_FAIL((!RETRY_PASS && h.sh_size <= MAX_NOTE_BYTES && scr_used + h.sh_size <= MAX_NOTE_BYTES) ? ST_RETRY_BIG_NOTES : ST_PLANNER_LIMIT);
-        break;
-      }
-#ifdef LB2_PLAN_TIMING
-      long long g0 = clock64();
-#endif
-      warp_g2s(sm.note_buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
-      __syncwarp();
-#ifdef LB2_PLAN_TIMING
-      if (lane == 0 && f == 0) printf("  notes g2s %u bytes: %lld cycles\n", (unsigned)h.sh_size, clock64() - g0);
-#endif
-      int err = 0;
-      uint8_t *dst = scr + SCR_NOTES + scr_used;
-      uint32_t ns = merge_build_notes(sm, (uint32_t)h.sh_size, dst, &err, lane);
-      if (err) { if (lane == 0) LB2_FAIL(err == 2 ? (RETRY_PASS ? ST_PLANNER_LIMIT : ST_RETRY_BIG_NOTES) : ST_BAD_NOTES); break; }
-      if (lane == 0) {
-        sm.new_size[i] = ns;
-        sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
-        sm.hdr_bytes += h.sh_size;
-      }
-      scr_used += (ns + 15u) & ~15u;
-      __syncwarp();
-    }
-  }
-  __syncwarp();
-  if (sm.fail) {
-    if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; if (sm.fail != ST_RETRY_BIG_NOTES) atomicAdd(&a.ctr->n_unsupported, 1u); }
-    return;
-  }
-
-  LB2_T(6);
-  // ---- F. which PT_LOAD carries each kept alloc section (lane-parallel), which phdrs survive (R11)
-  {
+  LB2_T(4);
+  // =====================================================================================================
+  // Three independent jobs on three warps: program headers + LOAD layout | note merging | .shstrtab
+  // =====================================================================================================
+  if (warp == 0) {
+    // ---- F2. the PT_LOAD that lays out each kept alloc section = the first LOAD carrying it
     int err = 0;
-    for (int i = 1 + lane; i < shnum; i += 32) {
-      if (!sm.keep[i] || !(sm.sh[i].sh_flags & SHF_ALLOC)) continue;
+    for (int i = lane; i < shnum; i += 32) {
+      if (!((allocmask >> i) & 1)) continue;
       int sg = -1;
       for (int j = 0; j < phnum; j++)
-        if (sm.ph[j].p_type == PT_LOAD && sec_in_seg(sm.sh[i], sm.ph[j])) { sg = j; break; }
+        if (sm.ph[j].p_type == PT_LOAD && ((sm.memb[j] >> i) & 1)) { sg = j; break; }
       if (sg < 0) err = 1;
       // gate: file offset and address of a loaded section move together (BFD: "lma adjusted" otherwise)
       else if (sm.sh[i].sh_type != SHT_NOBITS && sm.sh[i].sh_offset - sm.ph[sg].p_offset != sm.sh[i].sh_addr - sm.ph[sg].p_vaddr) err = 1;
       sm.seg[i] = (int8_t)sg;
     }
-    if (__ballot_sync(0xffffffffu, err)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-  }
-  __syncwarp();
-  {
-    int keepj = 1;
-    if (lane < phnum) {
-      uint64_t mm = 0, mb = 0;
-      if (sm.ph[lane].p_type == PT_LOAD)
-        for (int i = 1; i < shnum; i++)
-          if (sm.keep[i] && sm.seg[i] == lane) { mm |= 1ull << i; if (sm.sh[i].sh_type != SHT_NOBITS) mb |= 1ull << i; }
-      sm.seg_mask[lane] = mm;
-      sm.seg_bits[lane] = mb;
-      if (sm.ph[lane].p_type == PT_LOAD && sm.ph[lane].p_offset != 0 && !mm) keepj = 0;
-      sm.pkeep[lane] = (uint8_t)keepj;
-      sm.nph[lane] = sm.ph[lane];
-    }
-    unsigned km = __ballot_sync(0xffffffffu, lane < phnum && keepj);
-    if (lane == 0) sm.new_phnum = __popc(km);
-  }
-  __syncwarp();
-  const int new_phnum = sm.new_phnum;
-
-  LB2_T(7);
-  // ---- G. R10: PT_LOAD layout (sequential in the file cursor)
-  if (lane == 0) {
-    uint64_t cur = 64 + (uint64_t)new_phnum * 56, last_vaddr = 0;
-    for (int j = 0; j < phnum && !sm.fail; j++) {
-      const Phdr &p = sm.ph[j];
-      if (p.p_type != PT_LOAD || !sm.pkeep[j]) continue;
-      if (p.p_vaddr < last_vaddr) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); break; }
-      last_vaddr = p.p_vaddr;
-      const bool first = (p.p_offset == 0);
-      const bool contents = sm.seg_bits[j] != 0;
-      uint64_t new_off = 0;
-      if (!first) { uint64_t al = p.p_align ? p.p_align : 1; new_off = cur + ((p.p_vaddr - cur) % al); }
-      uint64_t off = first ? cur : new_off;
-      uint64_t mem_end = p.p_vaddr + (first ? cur : 0), file_end = off;
-      int idx = 0;
-      for (uint64_t mm = sm.seg_mask[j]; mm; mm &= mm - 1) {  // members in ascending section index
-        const int i = __ffsll((long long)mm) - 1;
-        const Shdr &h = sm.sh[i];
-        uint64_t want = new_off + (h.sh_addr - p.p_vaddr);
-        if (h.sh_type != SHT_NOBITS) {
-          if (want < off) { LB2_FAIL(ST_UNSUPPORTED_LAYOUT); break; }
-          off = want;
-          sm.new_off[i] = off;
-          off += sm.new_size[i];
-          file_end = off;
+    if (__ballot_sync(0xffffffffu, err)) { if (lane == 0) sm.fail = ST_UNSUPPORTED_LAYOUT; }
+    else {
+      // members per LOAD (R11: a LOAD without members, other than the header-bearing one, is deleted)
+      int keepj = 1;
+      if (lane < phnum) {
+        const Phdr &p = sm.ph[lane];
+        uint64_t mm = 0;
+        if (p.p_type == PT_LOAD) {
+          uint64_t earlier = 0;
+          for (int l = 0; l < lane; l++) if (sm.ph[l].p_type == PT_LOAD) earlier |= sm.memb[l];
+          mm = sm.memb[lane] & allocmask & ~earlier;
+        }
+        const uint64_t mb = mm & ~nobitsmask;
+        sm.seg_mask[lane] = mm;
+        sm.seg_bits[lane] = mb;
+        if (p.p_type == PT_LOAD && p.p_offset != 0 && !mm) keepj = 0;
+        sm.pkeep[lane] = (uint8_t)keepj;
+        sm.nph[lane] = p;
+        // per-LOAD extents relative to the LOAD's own start: everything the cursor chain below needs
+        uint64_t rel_end = 0, mem_top = 0;
+        if (p.p_type == PT_LOAD && keepj) {
+          if (mb) { const int lb = 63 - __clzll((long long)mb); rel_end = (sm.sh[lb].sh_addr - p.p_vaddr) + sm.sh[lb].sh_size; }
+          for (uint64_t q = mm; q; q &= q - 1) {
+            const int i = __ffsll((long long)q) - 1;
+            const Shdr &h = sm.sh[i];
+            if (!(h.sh_type == SHT_NOBITS && (h.sh_flags & SHF_TLS))) { const uint64_t e = h.sh_addr + h.sh_size; if (e > mem_top) mem_top = e; }
+          }
+        }
+        sm.load_rel_end[lane] = rel_end;
+        sm.load_mem_top[lane] = mem_top;
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, lane < phnum && keepj);
+      const int new_phnum = __popc(km);
+      if (lane == 0) sm.new_phnum = new_phnum;
+      __syncwarp();
+      // ---- G. R10: the file cursor runs over the LOADs in order (a handful of values per LOAD)
+      if (lane == 0) {
+        uint64_t cur = 64 + (uint64_t)new_phnum * 56, last_vaddr = 0;
+        for (int j = 0; j < phnum; j++) {
+          const Phdr &p = sm.ph[j];
+          if (p.p_type != PT_LOAD || !sm.pkeep[j]) continue;
+          if (p.p_vaddr < last_vaddr) { sm.fail = ST_UNSUPPORTED_LAYOUT; break; }
+          last_vaddr = p.p_vaddr;
+          const bool first = (p.p_offset == 0);
+          const bool contents = sm.seg_bits[j] != 0;
+          uint64_t new_off = 0;
+          if (!first) { const uint64_t al = p.p_align ? p.p_align : 1; new_off = cur + ((p.p_vaddr - cur) & (al - 1)); }  // p_align is a power of two (gate)
+          const uint64_t base_off = first ? cur : new_off;
+          const uint64_t file_end = contents ? new_off + sm.load_rel_end[j] : base_off;
+          uint64_t mem_end = p.p_vaddr + (first ? cur : 0);
+          if (sm.load_mem_top[j] > mem_end) mem_end = sm.load_mem_top[j];
+          Phdr &q = sm.nph[j];
+          q.p_offset = new_off;
+          if (!contents && !first) {
+            const uint64_t al = p.p_align > 0x1000 ? p.p_align : 0x1000;
+            q.p_offset = cur & (al - 1);
+            q.p_filesz = 0;
+          } else {
+            q.p_filesz = file_end - new_off;
+          }
+          q.p_memsz = mem_end - p.p_vaddr;
+          sm.load_newoff[j] = new_off;
+          sm.load_base[j] = base_off;
+          if (contents || first) cur = file_end;
+        }
+        sm.cur = cur;
+      }
+      __syncwarp();
+      // every member section's new offset follows from its LOAD's; the order checks of the sequential
+      // walk (a section may not start before the previous one ended) are per-section comparisons
+      if (!sm.fail) {
+        int bad = 0;
+        for (int i = lane; i < shnum; i += 32) {
+          if (!((allocmask >> i) & 1)) continue;
+          const int j = sm.seg[i];
+          if (!sm.pkeep[j]) continue;
+          const Phdr &p = sm.ph[j];
+          const uint64_t lo = sm.load_newoff[j];
+          const Shdr &h = sm.sh[i];
+          const uint64_t want = lo + (h.sh_addr - p.p_vaddr);
+          const uint64_t before = (1ull << i) - 1;
+          const uint64_t prev_bits = sm.seg_bits[j] & before, prev_any = sm.seg_mask[j] & before;
+          uint64_t floor_off;  // the cursor of the sequential walk when it reaches this section
+          if (prev_bits) { const int pb = 63 - __clzll((long long)prev_bits); floor_off = lo + (sm.sh[pb].sh_addr - p.p_vaddr) + sm.sh[pb].sh_size; }
+          else if (prev_any) { const int pf = __ffsll((long long)sm.seg_mask[j]) - 1; floor_off = lo + (sm.sh[pf].sh_addr - p.p_vaddr); }
+          else floor_off = (h.sh_type != SHT_NOBITS) ? sm.load_base[j] : want;
+          if (h.sh_type != SHT_NOBITS) {
+            if (want < floor_off) bad = 1;
+            sm.new_off[i] = want;
+          } else {
+            sm.new_off[i] = floor_off;
+          }
+        }
+        if (__ballot_sync(0xffffffffu, bad)) { if (lane == 0) sm.fail = ST_UNSUPPORTED_LAYOUT; }
+      }
+      __syncwarp();
+      // ---- H. R12: every other program header, one per lane
+      int gate_fail = 0;
+      if (!sm.fail && lane < phnum && sm.pkeep[lane] && sm.ph[lane].p_type != PT_LOAD) {
+        const int j = lane;
+        const Phdr &p = sm.ph[j];
+        Phdr &q = sm.nph[j];
+        const uint32_t t = p.p_type;
+        const uint64_t mine = sm.memb[j];
+        if (t == PT_PHDR) {
+          q.p_filesz = q.p_memsz = (uint64_t)new_phnum * 56;
         } else {
-          if (idx == 0) off = want;
-          sm.new_off[i] = off;
-        }
-        if (!(h.sh_type == SHT_NOBITS && (h.sh_flags & SHF_TLS))) {
-          uint64_t e = h.sh_addr + h.sh_size;
-          if (e > mem_end) mem_end = e;
-        }
-        idx++;
-      }
-      Phdr &q = sm.nph[j];
-      q.p_offset = new_off;
-      if (!contents && !first) {
-        uint64_t al = p.p_align > 0x1000 ? p.p_align : 0x1000;
-        q.p_offset = cur % al;
-        q.p_filesz = 0;
-      } else {
-        q.p_filesz = file_end - new_off;
-      }
-      q.p_memsz = mem_end - p.p_vaddr;
-      if (contents || first) cur = file_end;
-    }
-    sm.cur = cur;
-  }
-  __syncwarp();
-  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-
-  LB2_T(8);
-  // ---- H. R12: every other program header, one per lane
-  int gate_fail = 0;
-  if (lane < phnum && sm.pkeep[lane] && sm.ph[lane].p_type != PT_LOAD) {
-    const int j = lane;
-    const Phdr &p = sm.ph[j];
-    Phdr &q = sm.nph[j];
-    const uint32_t t = p.p_type;
-    if (t == PT_PHDR) {
-      q.p_filesz = q.p_memsz = (uint64_t)new_phnum * 56;
-    } else {
-      int first = -1, last_bits = -1;
-      uint64_t aend = 0, fend = 0;
-      bool any_alloc = false;
-      for (int i = 1; i < shnum; i++) {
-        const Shdr &h = sm.sh[i];
-        if (!sm.keep[i] || !sec_in_seg(h, p)) continue;
-        if (first < 0) first = i;
-        if (h.sh_type != SHT_NOBITS) { last_bits = i; if (h.sh_offset + h.sh_size > fend) fend = h.sh_offset + h.sh_size; }
-        if (h.sh_flags & SHF_ALLOC) { any_alloc = true; if (h.sh_addr + h.sh_size > aend) aend = h.sh_addr + h.sh_size; }
-      }
-      if (first >= 0 && t != PT_GNU_STACK && t != PT_GNU_RELRO && t != PT_TLS) {
-        // gate: a segment that carries sections must describe exactly their extent (BFD recomputes
-        // offset / filesz / memsz from the sections; natural files already agree)
-        const Shdr &hf = sm.sh[first];
-        if (any_alloc && (hf.sh_addr != p.p_vaddr || aend - p.p_vaddr != p.p_memsz)) gate_fail = 1;
-        if (hf.sh_type != SHT_NOBITS && hf.sh_offset != p.p_offset) gate_fail = 1;
-        if (fend && fend - p.p_offset != p.p_filesz) gate_fail = 1;
-      }
-      if (t == PT_GNU_STACK) { q.p_offset = 0; q.p_filesz = 0; }
-      else if (t == PT_GNU_RELRO) {
-        bool ok = false;
-        if (first >= 0) {
-          const uint64_t start = sm.sh[first].sh_addr, end = start + p.p_memsz;
-          for (int l = 0; l < phnum && !ok; l++) {
-            if (sm.ph[l].p_type != PT_LOAD || !sm.pkeep[l]) continue;
-            const uint64_t lm = sm.seg_mask[l];
-            if (!lm) continue;
-            const int lf = __ffsll((long long)lm) - 1, ll = 63 - __clzll((long long)lm);
-            const Shdr &hl = sm.sh[ll];
-            uint64_t lend = hl.sh_addr + ((hl.sh_type == SHT_NOBITS && (hl.sh_flags & SHF_TLS)) ? 0 : hl.sh_size);
-            if (!(lend > start && sm.sh[lf].sh_addr < end)) continue;
-            for (uint64_t mm = lm; mm; mm &= mm - 1) {
-              const int i = __ffsll((long long)mm) - 1;
-              const Shdr &h = sm.sh[i];
-              if (h.sh_addr >= start && h.sh_addr < end && h.sh_size != 0) {
-                q.p_vaddr = h.sh_addr;
-                q.p_paddr = h.sh_addr + (sm.ph[l].p_paddr - sm.ph[l].p_vaddr);
-                q.p_offset = sm.new_off[i];
-                q.p_memsz = end - q.p_vaddr;
-                q.p_filesz = q.p_memsz;
-                const Phdr &nl = sm.nph[l];
-                if (q.p_filesz > nl.p_vaddr + nl.p_filesz - q.p_vaddr) q.p_filesz = nl.p_vaddr + nl.p_filesz - q.p_vaddr;
-                ok = true;
+          const int first = mine ? __ffsll((long long)mine) - 1 : -1;
+          int last_bits = -1;
+          uint64_t aend = 0, fend = 0;
+          bool any_alloc = false;
+          for (uint64_t mq = mine; mq; mq &= mq - 1) {
+            const int i = __ffsll((long long)mq) - 1;
+            const Shdr &h = sm.sh[i];
+            if (h.sh_type != SHT_NOBITS) { last_bits = i; if (h.sh_offset + h.sh_size > fend) fend = h.sh_offset + h.sh_size; }
+            if (h.sh_flags & SHF_ALLOC) { any_alloc = true; if (h.sh_addr + h.sh_size > aend) aend = h.sh_addr + h.sh_size; }
+          }
+          if (first >= 0 && t != PT_GNU_STACK && t != PT_GNU_RELRO && t != PT_TLS) {
+            // gate: a segment that carries sections must describe exactly their extent (BFD recomputes
+            // offset / filesz / memsz from the sections; natural files already agree)
+            const Shdr &hf = sm.sh[first];
+            if (any_alloc && (hf.sh_addr != p.p_vaddr || aend - p.p_vaddr != p.p_memsz)) gate_fail = 1;
+            if (hf.sh_type != SHT_NOBITS && hf.sh_offset != p.p_offset) gate_fail = 1;
+            if (fend && fend - p.p_offset != p.p_filesz) gate_fail = 1;
+          }
+          if (t == PT_GNU_STACK) { q.p_offset = 0; q.p_filesz = 0; }
+          else if (t == PT_GNU_RELRO) {
+            bool ok = false;
+            if (first >= 0) {
+              const uint64_t start = sm.sh[first].sh_addr, end = start + p.p_memsz;
+              for (int l = 0; l < phnum && !ok; l++) {
+                if (sm.ph[l].p_type != PT_LOAD || !sm.pkeep[l]) continue;
+                const uint64_t lm = sm.seg_mask[l];
+                if (!lm) continue;
+                const int lf = __ffsll((long long)lm) - 1, ll = 63 - __clzll((long long)lm);
+                const Shdr &hl = sm.sh[ll];
+                uint64_t lend = hl.sh_addr + ((hl.sh_type == SHT_NOBITS && (hl.sh_flags & SHF_TLS)) ? 0 : hl.sh_size);
+                if (!(lend > start && sm.sh[lf].sh_addr < end)) continue;
+                for (uint64_t mm = lm; mm; mm &= mm - 1) {
+                  const int i = __ffsll((long long)mm) - 1;
+                  const Shdr &h = sm.sh[i];
+                  if (h.sh_addr >= start && h.sh_addr < end && h.sh_size != 0) {
+                    q.p_vaddr = h.sh_addr;
+                    q.p_paddr = h.sh_addr + (sm.ph[l].p_paddr - sm.ph[l].p_vaddr);
+                    q.p_offset = sm.new_off[i];
+                    q.p_memsz = end - q.p_vaddr;
+                    q.p_filesz = q.p_memsz;
+                    const Phdr &nl = sm.nph[l];
+                    if (q.p_filesz > nl.p_vaddr + nl.p_filesz - q.p_vaddr) q.p_filesz = nl.p_vaddr + nl.p_filesz - q.p_vaddr;
+                    ok = true;
+                    break;
+                  }
+                }
                 break;
               }
             }
-            break;
+            if (!ok) { q.p_type = 0; q.p_flags = 0; q.p_offset = q.p_vaddr = q.p_paddr = q.p_filesz = q.p_memsz = q.p_align = 0; }
+          } else if (first < 0) {
+            q.p_offset = 0; q.p_filesz = 0; q.p_memsz = 0;
+          } else {
+            q.p_offset = sm.new_off[first];
+            q.p_filesz = 0;
+            if (t == PT_TLS) {  // p_memsz := address extent of .tdata/.tbss (gold rounds its value up)
+              uint64_t end = p.p_vaddr;
+              for (uint64_t mq = mine; mq; mq &= mq - 1) {
+                const int i = __ffsll((long long)mq) - 1;
+                if (sm.sh[i].sh_addr + sm.sh[i].sh_size > end) end = sm.sh[i].sh_addr + sm.sh[i].sh_size;
+              }
+              q.p_memsz = end - p.p_vaddr;
+            }
+            if (last_bits >= 0) {
+              q.p_filesz = sm.new_off[last_bits] - q.p_offset + sm.new_size[last_bits];
+              if (t == PT_NOTE && (sm.sh[last_bits].sh_flags & SHF_ALLOC)) q.p_memsz = q.p_filesz;
+            }
           }
         }
-        if (!ok) { q.p_type = 0; q.p_flags = 0; q.p_offset = q.p_vaddr = q.p_paddr = q.p_filesz = q.p_memsz = q.p_align = 0; }
-      } else if (first < 0) {
-        q.p_offset = 0; q.p_filesz = 0; q.p_memsz = 0;
-      } else {
-        q.p_offset = sm.new_off[first];
-        q.p_filesz = 0;
-        if (t == PT_TLS) {  // p_memsz := address extent of .tdata/.tbss (gold rounds its value up)
-          uint64_t end = p.p_vaddr;
-          for (int i = 1; i < shnum; i++)
-            if (sm.keep[i] && sec_in_seg(sm.sh[i], p) && sm.sh[i].sh_addr + sm.sh[i].sh_size > end) end = sm.sh[i].sh_addr + sm.sh[i].sh_size;
-          q.p_memsz = end - p.p_vaddr;
-        }
-        if (last_bits >= 0) {
-          q.p_filesz = sm.new_off[last_bits] - q.p_offset + sm.new_size[last_bits];
-          if (t == PT_NOTE && (sm.sh[last_bits].sh_flags & SHF_ALLOC)) q.p_memsz = q.p_filesz;
-        }
       }
+      if (__ballot_sync(0xffffffffu, gate_fail)) { if (lane == 0 && !sm.fail) sm.fail = ST_UNSUPPORTED_LAYOUT; }
     }
-  }
-  __syncwarp();
-
-  LB2_T(9);
-  if (__ballot_sync(0xffffffffu, gate_fail)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-  // ---- I. R4 non-alloc sections packed behind the last allocated byte (align-then-add chain)
-  if (lane == 0) {
-    uint64_t cur = sm.cur;
-    for (int k = 1; k < nk; k++) {
+#ifdef LB2_PLAN_TIMING
+    if (lane == 0) sm.t_warp[0] = clock64();
+#endif
+  } else if (warp == 1) {
+    // ---- E. R9 build-attribute note merging (the new sizes feed the non-alloc layout after the join)
+    if (!(a.flags & 1u)) {
+      uint32_t scr_used = 0;
+      int nfail = 0;
+      for (uint64_t mq = keepmask & ~allocmask & ~1ull; mq && !nfail; mq &= mq - 1) {
+        const int i = __ffsll((long long)mq) - 1;
+        const Shdr &h = sm.sh[i];
+        if (h.sh_type != SHT_NOTE) continue;
+        if (!d_prefix(sm.names + h.sh_name, ".gnu.build.attributes")) continue;
+        if (h.sh_size > (uint64_t)MAX_NOTE_BYTES || scr_used + h.sh_size > MAX_NOTE_BYTES) { nfail = ST_PLANNER_LIMIT; break; }
+        int err = 0;
+        uint8_t *dst = scr + SCR_NOTES + scr_used;
+        const uint32_t ns = merge_build_notes(sm, in + h.sh_offset, (uint32_t)h.sh_size, dst, &err, lane);
+        if (err) { nfail = err == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES; break; }
+        if (lane == 0) {
+          sm.new_size[i] = ns;
+          sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
+          sm.note_hdr_bytes += h.sh_size;
+        }
+        scr_used += (ns + 15u) & ~15u;
+        __syncwarp();
+      }
+      if (nfail && lane == 0) sm.fail_e = nfail;  // kept apart from warp 0's verdict: notes are judged first, as in objcopy
+    }
+#ifdef LB2_PLAN_TIMING
+    if (lane == 0) sm.t_warp[1] = clock64();
+#endif
+  } else if (warp == 2) {
+    // ---- J. R6 .shstrtab: unique names (entry 0 = ".shstrtab"), reversed-string rank sort across
+    //         lanes, suffix merge, offsets in insertion order.
+    for (int k = 1 + lane; k < nk; k += 32) {
       const int i = sm.order[k];
-      const Shdr &h = sm.sh[i];
-      if (h.sh_flags & SHF_ALLOC) continue;
-      cur = align_up(cur, h.sh_addralign ? h.sh_addralign : 1);
-      sm.new_off[i] = cur;
-      if (h.sh_type != SHT_NOBITS) cur += sm.new_size[i];
-    }
-    sm.cur = cur;
-  }
-  __syncwarp();
-
-  LB2_T(10);
-  // ---- J. R6 .shstrtab: unique names (entry 0 = ".shstrtab"), reversed-string rank sort across
-  //         lanes, suffix merge, offsets in insertion order.
-  for (int k = 1 + lane; k < nk; k += 32) {
-    const int i = sm.order[k];
-    const char *nm = sm.names + sm.sh[i].sh_name;
-    int first = k;
-    const uint32_t hh = sm.name_hash[i];
-    if (sm.name_len[i] == 9 && d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
-    else for (int q = 1; q < k; q++) {
-      const int oi = sm.order[q];
-      if (sm.name_hash[oi] == hh && sm.name_len[oi] == sm.name_len[i] && d_streq(nm, sm.names + sm.sh[oi].sh_name)) { first = q; break; }
-    }
-    sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
-  }
-  __syncwarp();
-  // entries in insertion order: ".shstrtab", then every first occurrence of a non-empty name.  The entry
-  // index is the rank of the owner among owners (ballot + popc), no serial walk.
-  {
-    int base = 1;
-    if (lane == 0) { sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; }
-    for (int k0 = 0; k0 < nk; k0 += 32) {
-      const int k = k0 + lane;
-      bool owner = false;
-      int i = 0;
-      if (k >= 1 && k < nk) { i = sm.order[k]; owner = sm.piece[k] == k && sm.name_len[i] != 0; }
-      const unsigned m = __ballot_sync(0xffffffffu, owner);
-      if (owner) {
-        const int e = base + __popc(m & ((1u << lane) - 1));
-        sm.ent_str[e] = (uint16_t)sm.sh[i].sh_name;
-        sm.ent_len[e] = sm.name_len[i];
-        sm.sec_ent[i] = (uint8_t)e;
+      const char *nm = sm.names + sm.sh[i].sh_name;
+      int first = k;
+      const uint32_t hh = sm.name_hash[i];
+      if (sm.name_len[i] == 9 && d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
+      else for (int q = 1; q < k; q++) {
+        const int oi = sm.order[q];
+        if (sm.name_hash[oi] == hh && sm.name_len[oi] == sm.name_len[i] && d_streq(nm, sm.names + sm.sh[oi].sh_name)) { first = q; break; }
       }
-      base += __popc(m);
-    }
-    if (lane == 0) sm.nent = base;
-  }
-  __syncwarp();
-  for (int k = 1 + lane; k < nk; k += 32) {
-    const int i = sm.order[k];
-    if (sm.name_len[i] == 0) sm.sec_ent[i] = 0xff;                                        // empty name -> sh_name 0
-    else if (sm.piece[k] != k) sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
-  }
-  const int nent = sm.nent;
-  // reversed-suffix keys: the last 8 characters, last one most significant, zero padded -- an integer compare
-  // of two keys is elf-strtab.c's strrevcmp whenever one of the names is shorter than 8 or the keys differ
-  for (int e = lane; e < nent; e += 32) {
-    const char *nm = sm.names + sm.ent_str[e];
-    const int len = sm.ent_len[e];
-    uint64_t key = 0;
-    for (int q = 0; q < 8; q++) key = (key << 8) | (q < len ? (uint8_t)nm[len - 1 - q] : 0);
-    sm.ent_key[e] = key;
-    sm.ent_host[e] = -1;
-  }
-  __syncwarp();
-  for (int e = lane; e < nent; e += 32) {
-    const uint64_t ke = sm.ent_key[e];
-    const int le = sm.ent_len[e];
-    int r = 0;
-    for (int o = 0; o < nent; o++) {
-      if (o == e) continue;
-      const uint64_t ko = sm.ent_key[o];
-      bool less;
-      if (ko != ke) less = ko < ke;
-      else less = strrev_cmp(sm.names + sm.ent_str[o], sm.ent_len[o], sm.names + sm.ent_str[e], le) < 0;  // both >= 8 long
-      r += less;
-    }
-    sm.ent_sorted[r] = (uint8_t)e;  // names are unique => ranks are a permutation
-  }
-  __syncwarp();
-  if (lane == 0) {
-    int cur = sm.ent_sorted[nent - 1];
-    uint64_t kh = sm.ent_key[cur];
-    int lh = sm.ent_len[cur];
-    for (int s2 = nent - 2; s2 >= 0; s2--) {
-      const int c = sm.ent_sorted[s2];
-      const int lc = sm.ent_len[c];
-      const uint64_t kc = sm.ent_key[c];
-      bool suffix = lh > lc;
-      if (suffix) {
-        if (lc <= 8) suffix = (lc == 8 ? kh == kc : (kh >> (8 * (8 - lc))) == (kc >> (8 * (8 - lc))));
-        else {
-          const char *hs = sm.names + sm.ent_str[cur] + (lh - lc), *cs = sm.names + sm.ent_str[c];
-          for (int q = 0; q < lc; q++) if (hs[q] != cs[q]) { suffix = false; break; }
-        }
-      }
-      if (suffix) sm.ent_host[c] = (int16_t)cur;
-      else { cur = c; kh = kc; lh = lc; }
-    }
-  }
-  __syncwarp();
-  {
-    // offsets of the non-merged names: exclusive scan of (len + 1) in insertion order, 32 entries per step
-    uint32_t run = 1;
-    for (int e0 = 0; e0 < nent; e0 += 32) {
-      const int e = e0 + lane;
-      const uint32_t v = (e < nent && sm.ent_host[e] < 0) ? sm.ent_len[e] + 1u : 0u;
-      uint32_t inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      if (e < nent && sm.ent_host[e] < 0) sm.ent_off[e] = run + inc - v;
-      run += __shfl_sync(0xffffffffu, inc, 31);
+      sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
     }
     __syncwarp();
-    for (int e = lane; e < nent; e += 32)
-      if (sm.ent_host[e] >= 0) { const int h = sm.ent_host[e]; sm.ent_off[e] = sm.ent_off[h] + (sm.ent_len[h] - sm.ent_len[e]); }
-    if (lane == 0) {
-      sm.new_strsz = run;
-      // R5
-      sm.shstr_off = sm.cur;
-      sm.new_shoff = align_up(sm.cur + run, 8);
-      sm.total = sm.new_shoff + (uint64_t)(nk + 1) * 64;
+    // entries in insertion order: ".shstrtab", then every first occurrence of a non-empty name.  The entry
+    // index is the rank of the owner among owners (ballot + popc), no serial walk.
+    {
+      int ebase = 1;
+      if (lane == 0) { sm.ent_str[0] = (uint16_t)strsz; sm.ent_len[0] = 9; }
+      for (int k0 = 0; k0 < nk; k0 += 32) {
+        const int k = k0 + lane;
+        bool owner = false;
+        int i = 0;
+        if (k >= 1 && k < nk) { i = sm.order[k]; owner = sm.piece[k] == k && sm.name_len[i] != 0; }
+        const unsigned m = __ballot_sync(0xffffffffu, owner);
+        if (owner) {
+          const int e = ebase + __popc(m & ((1u << lane) - 1));
+          sm.ent_str[e] = (uint16_t)sm.sh[i].sh_name;
+          sm.ent_len[e] = sm.name_len[i];
+          sm.sec_ent[i] = (uint8_t)e;
+        }
+        ebase += __popc(m);
+      }
+      if (lane == 0) sm.nent = ebase;
     }
+    __syncwarp();
+    for (int k = 1 + lane; k < nk; k += 32) {
+      const int i = sm.order[k];
+      if (sm.name_len[i] == 0) sm.sec_ent[i] = 0xff;                                        // empty name -> sh_name 0
+      else if (sm.piece[k] != k) sm.sec_ent[i] = sm.piece[k] == 0 ? 0 : sm.sec_ent[sm.order[sm.piece[k]]];
+    }
+    const int nent = sm.nent;
+    // reversed-suffix keys: the last 8 characters, last one most significant, zero padded -- an integer compare
+    // of two keys is elf-strtab.c's strrevcmp whenever one of the names is shorter than 8 or the keys differ
+    for (int e = lane; e < nent; e += 32) {
+      const char *nm = sm.names + sm.ent_str[e];
+      const int len = sm.ent_len[e];
+      uint64_t key = 0;
+      for (int q = 0; q < 8; q++) key = (key << 8) | (q < len ? (uint8_t)nm[len - 1 - q] : 0);
+      sm.ent_key[e] = key;
+    }
+    __syncwarp();
+    for (int e = lane; e < nent; e += 32) {
+      const uint64_t ke = sm.ent_key[e];
+      const int le = sm.ent_len[e];
+      int r = 0;
+      for (int o = 0; o < nent; o++) {
+        if (o == e) continue;
+        const uint64_t ko = sm.ent_key[o];
+        bool less;
+        if (ko != ke) less = ko < ke;
+        else less = strrev_cmp(sm.names + sm.ent_str[o], sm.ent_len[o], sm.names + sm.ent_str[e], le) < 0;  // both >= 8 long
+        r += less;
+      }
+      sm.ent_sorted[r] = (uint8_t)e;  // names are unique => ranks are a permutation
+      sm.ent_pos[e] = (uint8_t)r;
+    }
+    __syncwarp();
+    // suffix merge.  BFD walks the sorted array from the end keeping the last name that was not merged
+    // ("host") and merges a name that is a suffix of the host.  Sorted by reversed string, a name is a suffix
+    // of the host exactly when it is a suffix of its immediate successor (everything between a prefix and a
+    // string sorts as an extension of that prefix), so the merged flag is a per-position test and the host is
+    // the nearest non-merged position above.
+    for (int s0 = 0; s0 < nent; s0 += 32) {
+      const int s2 = s0 + lane;
+      bool merged = false;
+      if (s2 < nent - 1) {
+        const int c = sm.ent_sorted[s2], hn = sm.ent_sorted[s2 + 1];
+        const int lc = sm.ent_len[c], lh = sm.ent_len[hn];
+        const uint64_t kc = sm.ent_key[c], kh = sm.ent_key[hn];
+        bool suffix = lh > lc;
+        if (suffix) {
+          if (lc <= 8) suffix = (lc == 8 ? kh == kc : (lc == 0 ? true : (kh >> (8 * (8 - lc))) == (kc >> (8 * (8 - lc)))));
+          else {
+            const char *hs = sm.names + sm.ent_str[hn] + (lh - lc), *cs = sm.names + sm.ent_str[c];
+            for (int q = 0; q < lc; q++) if (hs[q] != cs[q]) { suffix = false; break; }
+          }
+        }
+        merged = suffix;
+      }
+      if (s2 < nent) sm.piece[s2] = merged ? 1 : 0;   // (piece[] is free again: reused as the merged flag per sorted position)
+    }
+    __syncwarp();
+    for (int e = lane; e < nent; e += 32) {
+      int s2 = sm.ent_pos[e];
+      if (!sm.piece[s2]) { sm.ent_host[e] = -1; continue; }
+      do { s2++; } while (sm.piece[s2]);   // the last position is never merged
+      sm.ent_host[e] = (int16_t)sm.ent_sorted[s2];
+    }
+    __syncwarp();
+    {
+      // offsets of the non-merged names: exclusive scan of (len + 1) in insertion order, 32 entries per step
+      uint32_t run = 1;
+      for (int e0 = 0; e0 < nent; e0 += 32) {
+        const int e = e0 + lane;
+        const uint32_t v = (e < nent && sm.ent_host[e] < 0) ? sm.ent_len[e] + 1u : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (e < nent && sm.ent_host[e] < 0) sm.ent_off[e] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      __syncwarp();
+      for (int e = lane; e < nent; e += 32)
+        if (sm.ent_host[e] >= 0) { const int h = sm.ent_host[e]; sm.ent_off[e] = sm.ent_off[h] + (sm.ent_len[h] - sm.ent_len[e]); }
+      if (lane == 0) sm.new_strsz = run;
+      // blob: zero, then every non-merged name at its offset
+      if (run <= MAX_STR + 16) {
+        for (uint32_t i = lane; i < ((run + 15u) & ~15u); i += 32) scr[SCR_STR + i] = 0;
+        __syncwarp();
+        for (int e = lane; e < nent; e += 32)
+          if (sm.ent_host[e] < 0) {
+            const char *s = sm.names + sm.ent_str[e];
+            for (int q = 0; q < sm.ent_len[e]; q++) scr[SCR_STR + sm.ent_off[e] + q] = (uint8_t)s[q];
+          }
+      }
+    }
+#ifdef LB2_PLAN_TIMING
+    if (lane == 0) sm.t_warp[2] = clock64();
+#endif
   }
-  __syncwarp();
+  __syncthreads();
+  if (sm.fail_e || sm.fail) LB2_REJECT(sm.fail_e ? sm.fail_e : sm.fail);
+  LB2_T(5);
+
+  // ---- I. R4 non-alloc sections packed behind the last allocated byte (align-then-add chain over the
+  //         few kept non-alloc sections), R5 .shstrtab and section-table position
+  if (tid == 0) {
+    uint64_t cur = sm.cur;
+    if (!sm.need_hoist) {
+      for (uint64_t mq = keepmask & ~allocmask & ~1ull; mq; mq &= mq - 1) {   // index order == output order
+        const int i = __ffsll((long long)mq) - 1;
+        const Shdr &h = sm.sh[i];
+        cur = align_up(cur, h.sh_addralign ? h.sh_addralign : 1);
+        sm.new_off[i] = cur;
+        if (h.sh_type != SHT_NOBITS) cur += sm.new_size[i];
+      }
+    } else {
+      for (int k = 1; k < nk; k++) {
+        const int i = sm.order[k];
+        const Shdr &h = sm.sh[i];
+        if (h.sh_flags & SHF_ALLOC) continue;
+        cur = align_up(cur, h.sh_addralign ? h.sh_addralign : 1);
+        sm.new_off[i] = cur;
+        if (h.sh_type != SHT_NOBITS) cur += sm.new_size[i];
+      }
+    }
+    sm.cur = cur;
+    sm.shstr_off = cur;
+    sm.new_shoff = align_up(cur + sm.new_strsz, 8);
+    sm.total = sm.new_shoff + (uint64_t)(nk + 1) * 64;
+    sm.hdr_bytes += sm.note_hdr_bytes;
+  }
+  __syncthreads();
   const uint32_t new_strsz = sm.new_strsz;
+  const int new_phnum = sm.new_phnum;
   // sanity bound on the stripped size: re-layout can add LOAD alignment padding (at most a few MB per segment),
   // never more; a larger value means wrapped address arithmetic on a hostile or corrupt file.  Also keeps the
   // per-file tile count far inside 32 bits.
-  if (sm.total > n + (65ull << 20)) { if (lane == 0) { a.status[f] = ST_UNSUPPORTED_LAYOUT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-  if (new_strsz > MAX_STR + 16) { if (lane == 0) { a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-  // blob: zero, then every non-merged name at its offset
-  for (uint32_t i = lane; i < ((new_strsz + 15u) & ~15u); i += 32) scr[SCR_STR + i] = 0;
-  __syncwarp();
-  for (int e = lane; e < nent; e += 32)
-    if (sm.ent_host[e] < 0) {
-      const char *s = sm.names + sm.ent_str[e];
-      for (int q = 0; q < sm.ent_len[e]; q++) scr[SCR_STR + sm.ent_off[e] + q] = (uint8_t)s[q];
-    }
+  if (sm.total > n + (65ull << 20)) LB2_REJECT(ST_UNSUPPORTED_LAYOUT);
+  if (new_strsz > MAX_STR + 16) LB2_REJECT(ST_PLANNER_LIMIT);
 
-  LB2_T(11);
-  // ---- K. R7 new section-header table (one header per lane-iteration), R8 Ehdr, new Phdr table
-  for (int k = lane; k <= nk; k += 32) {
+  LB2_T(6);
+  // ---- K. R7 new section-header table (one header per thread), R8 Ehdr, new Phdr table
+  if (tid <= nk) {
+    const int k = tid;
     Shdr h;
     if (k == 0) {
       h.sh_name = 0; h.sh_type = 0; h.sh_flags = 0; h.sh_addr = 0; h.sh_offset = 0; h.sh_size = 0; h.sh_link = 0;
@@ -1135,9 +1286,9 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       h.sh_name = sm.sec_ent[i] == 0xff ? 0 : sm.ent_off[sm.sec_ent[i]];
       h.sh_offset = sm.new_off[i];
       h.sh_size = sm.new_size[i];
-      if (h.sh_link && h.sh_link < (uint32_t)shnum) h.sh_link = sm.keep[h.sh_link] ? sm.new_index[h.sh_link] : 0;
+      if (h.sh_link && h.sh_link < (uint32_t)shnum) h.sh_link = ((keepmask >> h.sh_link) & 1) ? sm.new_index[h.sh_link] : 0;
       if ((h.sh_flags & SHF_INFO_LINK) && h.sh_info && h.sh_info < (uint32_t)shnum)
-        h.sh_info = sm.keep[h.sh_info] ? sm.new_index[h.sh_info] : 0;
+        h.sh_info = ((keepmask >> h.sh_info) & 1) ? sm.new_index[h.sh_info] : 0;
       if ((h.sh_type == SHT_REL || h.sh_type == SHT_RELA) && sm.sh[i].sh_link == 0) {
         // assign_section_numbers(): an allocated reloc section without a symbol table gets .dynsym
         for (int q = 1; q < nk; q++) {
@@ -1184,49 +1335,51 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
     }
     *reinterpret_cast<Shdr *>(scr + SCR_SHDR + (uint32_t)k * 64) = h;
   }
-  if (lane == 0) {
+  if (tid >= 96 && tid - 96 < phnum && sm.pkeep[tid - 96]) {   // warp 3: the surviving program headers, compacted
+    const int j = tid - 96;
+    int slot = 0;
+    for (int l = 0; l < j; l++) slot += sm.pkeep[l];
+    const uint64_t *s8 = reinterpret_cast<const uint64_t *>(&sm.nph[j]);
+    uint64_t *d8 = reinterpret_cast<uint64_t *>(scr + 64 + (uint32_t)slot * 56);
+    for (int q = 0; q < 7; q++) d8[q] = s8[q];
+  }
+  if (tid == 95) {
     Ehdr ne = sm.eh;
     ne.e_shoff = sm.new_shoff;
     ne.e_shnum = (uint16_t)(nk + 1);
     ne.e_shstrndx = (uint16_t)nk;
     ne.e_phnum = (uint16_t)new_phnum;
     *reinterpret_cast<Ehdr *>(scr + SCR_EHDR) = ne;
-    uint32_t w = 64;
-    for (int j = 0; j < phnum; j++)
-      if (sm.pkeep[j]) {
-        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(&sm.nph[j]);
-        uint64_t *d8 = reinterpret_cast<uint64_t *>(scr + w);
-        for (int q = 0; q < 7; q++) d8[q] = s8[q];
-        w += 56;
-      }
   }
 
-  LB2_T(12);
+  LB2_T(7);
   // ---- L. extents: every output byte is produced exactly once -- copied from the input arena,
   //         copied from the scratch slot, or zero-filled (BFD leaves gaps as file holes).
+  // pieces = [headers] + content sections sorted by new offset + [.shstrtab] + [section table].  Rank sort,
+  // one kept section per thread (the keys are distinct unless sections overlap, which the gap check rejects).
   {
-    // pieces = [headers] + content sections sorted by new offset + [.shstrtab] + [section table].  Rank sort
-    // across lanes (the keys are distinct unless sections overlap, which the gap check below rejects).
-    int np = 0;
-    for (int k0 = 0; k0 < nk; k0 += 32) {
-      const int k = k0 + lane;
-      bool content = false;
-      int i = 0;
-      if (k >= 1 && k < nk) { i = sm.order[k]; content = sm.sh[i].sh_type != SHT_NOBITS && sm.new_size[i] != 0; }
-      if (content) {
-        const uint64_t mine = sm.new_off[i];
-        int r = 0;
-        for (int q = 1; q < nk; q++) {
-          const int oi = sm.order[q];
-          if (q == k || sm.sh[oi].sh_type == SHT_NOBITS || sm.new_size[oi] == 0) continue;
-          const uint64_t o = sm.new_off[oi];
-          r += (o < mine) || (o == mine && q < k);
-        }
-        sm.piece[1 + r] = (uint8_t)i;
+    bool content = false;
+    int i = 0;
+    if (tid >= 1 && tid < nk) { i = sm.order[tid]; content = sm.sh[i].sh_type != SHT_NOBITS && sm.new_size[i] != 0; }
+    if (content) {
+      const uint64_t mine = sm.new_off[i];
+      int r = 0;
+      for (int q = 1; q < nk; q++) {
+        const int oi = sm.order[q];
+        if (q == tid || sm.sh[oi].sh_type == SHT_NOBITS || sm.new_size[oi] == 0) continue;
+        const uint64_t o = sm.new_off[oi];
+        r += (o < mine) || (o == mine && q < tid);
       }
-      np += __popc(__ballot_sync(0xffffffffu, content));
+      sm.piece[1 + r] = (uint8_t)i;
     }
-    __syncwarp();
+    if (tid < 64) {
+      const unsigned m = __ballot_sync(0xffffffffu, content);
+      if (lane == 0) sm.keep32[warp] = __popc(m);   // (keep32 is free: keepmask lives in registers)
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int np = (int)(sm.keep32[0] + sm.keep32[1]);
     const int total_pieces = np + 3;  // + headers, .shstrtab, section table
     auto piece_of = [&](int q, uint64_t &src, uint64_t &dst, uint64_t &len) {
       if (q == 0) { src = reinterpret_cast<uint64_t>(scr + SCR_EHDR); dst = 0; len = 64 + (uint64_t)new_phnum * 56; }
@@ -1234,8 +1387,10 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       else if (q == np + 1) { src = reinterpret_cast<uint64_t>(scr + SCR_STR); dst = sm.shstr_off; len = new_strsz; }
       else { src = reinterpret_cast<uint64_t>(scr + SCR_SHDR); dst = sm.new_shoff; len = (uint64_t)(nk + 1) * 64; }
     };
+    ExtWork &x = sm.u.x;
     int ne = 0, bad = 0;
     unsigned long long copy_bytes = 0;
+    uint32_t running = 0;
     for (int q0 = 0; q0 < total_pieces; q0 += 32) {
       const int q = q0 + lane;
       uint64_t src = 0, dst = 0, len = 0, prev_end = 0;
@@ -1248,55 +1403,55 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       }
       const bool gap = valid && dst > prev_end;
       const unsigned gm = __ballot_sync(0xffffffffu, gap);
+      // tile counts ride along: every extent gets its slot range in the file's tile list by a shuffle scan
+      uint32_t cnt_gap = 0, cnt = 0;
+      if (gap) cnt_gap = (uint32_t)((dst - 1) / TILE_BYTES - prev_end / TILE_BYTES + 1);
+      if (valid && len) cnt = (uint32_t)((dst + len - 1) / TILE_BYTES - dst / TILE_BYTES + 1);
+      uint32_t inc = cnt_gap + cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
       if (valid) {
         int at = ne + lane + __popc(gm & ((1u << lane) - 1));
-        if (gap) { sm.ext_src[at] = 0; sm.ext_dst[at] = prev_end; sm.ext_len[at] = dst - prev_end; at++; }  // file hole
-        sm.ext_src[at] = src; sm.ext_dst[at] = dst; sm.ext_len[at] = len;
+        uint32_t t0 = running + inc - (cnt_gap + cnt);
+        if (gap) { x.src[at] = 0; x.dst[at] = prev_end; x.len[at] = dst - prev_end; x.tiles[at] = t0; t0 += cnt_gap; at++; }  // file hole
+        x.src[at] = src; x.dst[at] = dst; x.len[at] = len; x.tiles[at] = t0;
         copy_bytes += len;
       }
+      running += __shfl_sync(0xffffffffu, inc, 31);
       const int nvalid = total_pieces - q0 < 32 ? total_pieces - q0 : 32;
       ne += nvalid + __popc(gm);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) copy_bytes += __shfl_xor_sync(0xffffffffu, copy_bytes, o);
-    if (__ballot_sync(0xffffffffu, bad)) { if (lane == 0) LB2_FAIL(ST_UNSUPPORTED_LAYOUT); }
-    if (lane == 0) { sm.n_ext = ne; sm.cur = copy_bytes; }
-  }
-  __syncwarp();
-  if (sm.fail) { if (lane == 0) { a.status[f] = sm.fail; a.out_size[f] = 0; atomicAdd(&a.ctr->n_unsupported, 1u); } return; }
-
-  LB2_T(13);
-  // ---- M. tiles: warp-shuffle prefix sum over the per-extent tile counts gives every extent its
-  //         slot range in the global tile list; one atomicAdd per file reserves the range.
-  const int n_ext = sm.n_ext;
-  __shared__ unsigned long long s_tile_base;
-  uint32_t running = 0;
-  for (int e0 = 0; e0 < n_ext; e0 += 32) {
-    const int e = e0 + lane;
-    uint32_t cnt = 0;
-    if (e < n_ext) {
-      const uint64_t d = sm.ext_dst[e], l = sm.ext_len[e];
-      cnt = (uint32_t)((d + l - 1) / TILE_BYTES - d / TILE_BYTES + 1);
+    const bool any_bad = __ballot_sync(0xffffffffu, bad) != 0;
+    if (lane == 0) {
+      sm.n_ext = ne; sm.copy_bytes = copy_bytes; sm.n_tiles = running;
+      if (any_bad) sm.fail = ST_UNSUPPORTED_LAYOUT;
+      else sm.tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);   // one atomicAdd per file reserves the range
     }
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    if (e < n_ext) sm.ext_tiles[e] = running + inc - cnt;  // exclusive prefix
-    running += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 0) s_tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);
-  __syncwarp();
-  const unsigned long long tile_base = s_tile_base;
-  if (tile_base + running > a.tile_cap) {
-    if (lane == 0) { a.ctr->overflow = 1; a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; }
+  __syncthreads();
+  if (sm.fail) LB2_REJECT(sm.fail);
+
+  LB2_T(8);
+  // ---- M. tiles: small extents go one per warp, big ones are written by the whole CTA
+  const int n_ext = sm.n_ext;
+  const unsigned long long tile_base = sm.tile_base;
+  if (tile_base + sm.n_tiles > a.tile_cap) {
+    if (tid == 0) { a.ctr->overflow = 1; a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; }
     return;
   }
   for (int e = 0; e < n_ext; e++) {
-    const uint64_t d = sm.ext_dst[e], l = sm.ext_len[e], s = sm.ext_src[e];
+    const uint64_t d = sm.u.x.dst[e], l = sm.u.x.len[e], s = sm.u.x.src[e];
+    if (l == 0) continue;
     const uint64_t t0 = d / TILE_BYTES;
     const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - t0 + 1);
-    Tile *out = a.tiles + tile_base + sm.ext_tiles[e];
-    for (uint32_t k = lane; k < cnt; k += 32) {
+    Tile *out = a.tiles + tile_base + sm.u.x.tiles[e];
+    uint32_t k, step;
+    if (cnt > 64) { k = tid; step = PLAN_THREADS; }
+    else if ((e & 3) == warp) { k = lane; step = 32; }
+    else continue;
+    for (; k < cnt; k += step) {
       uint64_t b = (t0 + k) * TILE_BYTES, en = b + TILE_BYTES;
       if (b < d) b = d;
       if (en > d + l) en = d + l;
@@ -1308,18 +1463,18 @@ __global__ void __launch_bounds__(32) lb2_plan_kernel(PlanArgs a) {
       out[k] = t;
     }
   }
-  LB2_T(14);
+  LB2_T(9);
 #ifdef LB2_PLAN_TIMING
-  if (lane == 0 && f == 0) {
-    printf("plan timing (cycles) retry=%d:", (int)RETRY_PASS);
-    for (int q = 1; q <= 14; q++) printf(" %c=%lld", q <= 13 ? 'A' + q - 1 : 'Z', t_[q] - t_[q - 1]);
-    printf(" total=%lld\n", t_[14] - t_[0]);
+  if (tid == 0 && f == 0) {
+    printf("plan timing (cycles): A=%lld B=%lld C=%lld D+F1=%lld [w0 PH=%lld w1 notes=%lld w2 strtab=%lld] join=%lld I=%lld K=%lld L=%lld M=%lld total=%lld\n",
+           t_[1] - t_[0], t_[2] - t_[1], t_[3] - t_[2], t_[4] - t_[3], sm.t_warp[0] - t_[4], sm.t_warp[1] - t_[4], sm.t_warp[2] - t_[4],
+           t_[5] - t_[4], t_[6] - t_[5], t_[7] - t_[6], t_[8] - t_[7], t_[9] - t_[8], t_[9] - t_[0]);
   }
 #endif
-  if (lane == 0) {
+  if (tid == 0) {
     a.out_size[f] = sm.total;
     a.status[f] = ST_OK;
-    atomicAdd(&a.ctr->copy_bytes, (unsigned long long)sm.cur);
+    atomicAdd(&a.ctr->copy_bytes, (unsigned long long)sm.copy_bytes);
     atomicAdd(&a.ctr->out_bytes, (unsigned long long)sm.total);
     atomicAdd(&a.ctr->header_bytes, (unsigned long long)sm.hdr_bytes);
     atomicAdd(&a.ctr->in_bytes, (unsigned long long)n);
@@ -1368,10 +1523,7 @@ __global__ void __launch_bounds__(1024) lb2_scan_kernel(const uint64_t *out_size
 
 void launch_plan(const PlanArgs &a, cudaStream_t s) {
   if (!a.n_files) return;
-  // common case: <= 1 KB / 52 notes of build attributes per section -> ~19 KB smem, 11 files per SM
-  lb2_plan_kernel<1024, 52, false><<<a.n_files, 32, 0, s>>>(a);
-  // files with larger note sections (annobin-built wheels): full-size workspace, everyone else exits at once
-  lb2_plan_kernel<MAX_NOTE_BYTES, MAX_NOTES, true><<<a.n_files, 32, 0, s>>>(a);
+  lb2_plan_kernel<<<a.n_files, PLAN_THREADS, 0, s>>>(a);  // one CTA per file, one launch for every file
 }
 void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, cudaStream_t s) {
   lb2_scan_kernel<<<1, 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr);

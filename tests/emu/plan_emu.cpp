@@ -1,5 +1,5 @@
 // plan_emu.cpp -- TEST HARNESS: runs the PRODUCT's device planner source (lambdipy_b200/csrc/plan.cu) on the
-// CPU by emulating one warp with 32 host threads (barrier-based __syncwarp / __ballot_sync / __shfl*), then
+// CPU by emulating one CTA (4 warps) with 128 host threads (barrier-based __syncthreads / __syncwarp / __ballot_sync / __shfl*), then
 // executes the emitted tile list with memcpy to materialise the stripped file.  It lets the CPU test-suite
 // (-m "not gpu") check the planner logic that ships in the CUDA library against the oracle and GNU strip
 // without a GPU.  It is NOT a CPU fallback: it lives under tests/, is built only by the tests, is never
@@ -12,42 +12,48 @@
 
 #include "cuda_runtime.h"  // the shim
 
-// ---- warp emulation state
+// ---- CTA emulation state: 4 warps of 32 host threads; warp collectives exchange through a per-warp slot
+//      array and barrier, __syncthreads is a barrier over all 128 threads
+static constexpr int EMU_THREADS = 128, EMU_WARPS = EMU_THREADS / 32;
 static thread_local uint3 threadIdx, blockIdx;
-static std::barrier<> *g_bar;
-static uint64_t g_xchg[32];
-static inline void __syncwarp() { g_bar->arrive_and_wait(); }
+static std::barrier<> *g_wbar[EMU_WARPS];
+static std::barrier<> *g_bbar;
+static uint64_t g_xchg[EMU_WARPS][32];
+#define EMU_W (threadIdx.x >> 5)
+#define EMU_L (threadIdx.x & 31)
+static inline void __syncwarp() { g_wbar[EMU_W]->arrive_and_wait(); }
+static inline void __syncthreads() { g_bbar->arrive_and_wait(); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
-  g_xchg[threadIdx.x] = pred ? 1 : 0;
-  g_bar->arrive_and_wait();
+  g_xchg[EMU_W][EMU_L] = pred ? 1 : 0;
+  g_wbar[EMU_W]->arrive_and_wait();
   unsigned m = 0;
-  for (int i = 0; i < 32; i++) m |= (unsigned)g_xchg[i] << i;
-  g_bar->arrive_and_wait();
+  for (int i = 0; i < 32; i++) m |= (unsigned)g_xchg[EMU_W][i] << i;
+  g_wbar[EMU_W]->arrive_and_wait();
   return m;
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
   uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
-  g_xchg[threadIdx.x] = raw;
-  g_bar->arrive_and_wait();
-  T r; memcpy(&r, &g_xchg[src & 31], sizeof r);
-  g_bar->arrive_and_wait();
+  g_xchg[EMU_W][EMU_L] = raw;
+  g_wbar[EMU_W]->arrive_and_wait();
+  T r; memcpy(&r, &g_xchg[EMU_W][src & 31], sizeof r);
+  g_wbar[EMU_W]->arrive_and_wait();
   return r;
 }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
   uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
-  g_xchg[threadIdx.x] = raw;
-  g_bar->arrive_and_wait();
+  g_xchg[EMU_W][EMU_L] = raw;
+  g_wbar[EMU_W]->arrive_and_wait();
   T r = v;
-  if ((int)threadIdx.x >= d) memcpy(&r, &g_xchg[threadIdx.x - d], sizeof r);
-  g_bar->arrive_and_wait();
+  if ((int)EMU_L >= d) memcpy(&r, &g_xchg[EMU_W][EMU_L - d], sizeof r);
+  g_wbar[EMU_W]->arrive_and_wait();
   return r;
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
   uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
-  g_xchg[threadIdx.x] = raw;
-  g_bar->arrive_and_wait();
-  T r; memcpy(&r, &g_xchg[(threadIdx.x ^ m) & 31], sizeof r);
-  g_bar->arrive_and_wait();
+  g_xchg[EMU_W][EMU_L] = raw;
+  g_wbar[EMU_W]->arrive_and_wait();
+  T r; memcpy(&r, &g_xchg[EMU_W][(EMU_L ^ m) & 31], sizeof r);
+  g_wbar[EMU_W]->arrive_and_wait();
   return r;
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
@@ -56,6 +62,7 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetc
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline long long clock64() { return 0; }
@@ -65,16 +72,20 @@ static inline long long clock64() { return 0; }
 
 using namespace lb2;
 
-template <int NB, int NN, bool RETRY> static void run_warp(const PlanArgs &a) {
-  std::barrier<> bar(32);
-  g_bar = &bar;
+static void run_block(const PlanArgs &a) {
+  std::barrier<> bbar(EMU_THREADS);
+  std::barrier<> w0(32), w1(32), w2(32), w3(32);
+  g_bbar = &bbar;
+  g_wbar[0] = &w0; g_wbar[1] = &w1; g_wbar[2] = &w2; g_wbar[3] = &w3;
   std::vector<std::thread> th;
-  for (int l = 0; l < 32; l++)
+  for (int l = 0; l < EMU_THREADS; l++)
     th.emplace_back([&, l] {
       threadIdx = uint3{(uint32_t)l, 0, 0};
       blockIdx = uint3{0, 0, 0};
-      lb2_plan_kernel<NB, NN, RETRY>(a);
-      bar.arrive_and_drop();  // lanes leave together (all early exits in the kernel are warp-uniform)
+      lb2_plan_kernel(a);
+      // threads leave together (every early exit of the kernel is taken by the whole CTA)
+      g_wbar[l >> 5]->arrive_and_drop();
+      bbar.arrive_and_drop();
     });
   for (auto &t : th) t.join();
 }
@@ -97,8 +108,7 @@ extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8
   PlanArgs a;
   a.in = arena; a.in_off = &in_off; a.in_size = &in_size; a.n_files = 1; a.flags = flags;
   a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr;
-  run_warp<1024, 52, false>(a);
-  if (status == ST_RETRY_BIG_NOTES) run_warp<MAX_NOTE_BYTES, MAX_NOTES, true>(a);
+  run_block(a);
   int rc = status;
   if (status == ST_OK && !ctr.overflow) {
     uint8_t *out = static_cast<uint8_t *>(malloc(out_size ? out_size : 1));

@@ -57,7 +57,25 @@ def main():
             res["ctx_create"].append({"import_s": a, "lb2_ctx_create_s": b, "lb2_tree_prepare_s": c})
         else:
             res["ctx_create"].append({"error": r.stderr[-300:]})
-    base = tempfile.mkdtemp(prefix="lb2_oneshot_", dir="/dev/shm")
+    # the reference executes the script it writes into the build directory: the tree must live on a
+    # filesystem mounted exec (/dev/shm is noexec on the GPU boxes)
+    base = None
+    for cand in ("/dev/shm", "/tmp", ROOT):
+        d = tempfile.mkdtemp(prefix="lb2_oneshot_", dir=cand)
+        probe = os.path.join(d, "x.sh")
+        with open(probe, "w") as f:
+            f.write("#!/bin/bash\nexit 0\n")
+        os.chmod(probe, 0o755)
+        try:
+            ok = subprocess.run([probe]).returncode == 0
+        except OSError:
+            ok = False
+        os.unlink(probe)
+        if ok:
+            base = d
+            break
+        shutil.rmtree(d, ignore_errors=True)
+    res["build_dir_fs"] = os.path.dirname(base)
     try:
         for name, roots in TREES.items():
             roots = [r for r in roots if os.path.isdir(os.path.join(sp, r))]
