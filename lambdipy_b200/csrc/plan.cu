@@ -14,8 +14,7 @@
 //   * the sequential parts that remain (LOAD cursor, non-alloc packing, note range inheritance) touch a
 //     handful of values each; the note sorts -- glibc's merge sort restated level by level -- compare
 //     register-resident keys and prefetch the next element of both runs;
-//   * one launch for every file: the note workspace (320 notes) aliases the extent arrays, note bytes are
-//     read through L1 straight from the arena.
+//   * one launch for every file: the note workspace (8 KB of note bytes, 320 notes) aliases the extent arrays.
 //
 // Replaces, per file, what the reference delegates to the external `strip` binary:
 // /root/reference/lambdipy/project_build.py:260.  Rules R1..R12: /root/repo/SURVEY.md 8(c).
@@ -46,6 +45,7 @@ struct __align__(16) DNote {
 static_assert(sizeof(DNote) == 32, "DNote is read as two 16-byte vectors");
 
 struct NoteWork {
+  __align__(16) uint8_t buf[MAX_NOTE_BYTES];  // the section's bytes: a dependent load from here costs ~30 cycles, from L2 ~300
   DNote notes[MAX_NOTES];
   uint64_t key[MAX_NOTES];   // bytes 3..10 of the name, big-endian packed, zero padded: decides most name comparisons
   uint16_t perm[MAX_NOTES], tmp[MAX_NOTES];
@@ -83,7 +83,8 @@ struct PlanSmem {
   uint8_t piece[MAX_SH + 1];
   uint16_t name_len[MAX_SH];     // strlen of each section's name
   uint32_t name_hash[MAX_SH];    // FNV-1a of each section's name: cheap inequality test
-  char names[MAX_STR + 16];
+  char names[MAX_STR + 48];      // + ".shstrtab" literal + slack for the 24-byte name loads
+  uint8_t name_kind[MAX_SH];     // 1: the section is called .dynstr, 2: .dynsym (what sh_link must point at)
   // build-attribute note workspace (phase E, warp 1) and the extent list (phases L/M) are never live together
   union { NoteWork n; ExtWork x; } u;
   // scalars shared by the CTA
@@ -93,6 +94,7 @@ struct PlanSmem {
   uint32_t strsz, new_strsz;
   uint64_t cur, shstr_off, new_shoff, total, hdr_bytes, note_hdr_bytes, copy_bytes;
   unsigned long long tile_base;
+  unsigned long long big_ext[3];  // bit e: extent e has more than 64 tiles (MAX_EXT = 140 extents)
   uint32_t n_tiles;
 #ifdef LB2_PLAN_TIMING
   long long t_warp[4];
@@ -120,10 +122,65 @@ __device__ __forceinline__ uint32_t d_hash(const char *s, int *len_out) {
   return h;
 }
 
+// ---- section names as packed words ------------------------------------------------------------------
+// Every rule on section names below is "equals L", "starts with L" or "is L or L.<suffix>" for a literal L
+// of at most 21 characters.  A thread packs the first 24 bytes of its section's name into three 64-bit
+// words once (bytes behind the terminating NUL forced to zero); each rule is then one or two masked integer
+// compares against compile-time constants -- no per-character loops, no divergence between the threads of
+// a warp that look at different names.  (Character loops cost ~5 cycles per dependent instruction on a
+// latency-bound warp: the string-compare version of this gate was a third of the kernel's critical path.)
+struct NameW { uint64_t w[3]; };
+struct Lit { uint64_t w[3]; int len; };
+template <int N> __host__ __device__ constexpr Lit lit(const char (&s)[N]) {
+  Lit l{{0, 0, 0}, N - 1};
+  for (int i = 0; i < N - 1; i++) l.w[i >> 3] |= (uint64_t)(uint8_t)s[i] << (8 * (i & 7));
+  return l;
+}
+__device__ __forceinline__ void name_words(const char *s, NameW &n) {  // s has >= 24 readable bytes
+  uint64_t w[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) v |= (uint64_t)(uint8_t)s[8 * k + q] << (8 * q);
+    w[k] = v;
+  }
+  bool ended = false;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (ended) { w[k] = 0; continue; }
+    const uint64_t z = (w[k] - 0x0101010101010101ull) & ~w[k] & 0x8080808080808080ull;  // lowest set bit: first zero byte
+    if (z) {
+      const int idx = (__ffsll((long long)z) - 1) >> 3;
+      w[k] &= idx ? (~0ull >> (8 * (8 - idx))) : 0ull;
+      ended = true;
+    }
+  }
+  n.w[0] = w[0]; n.w[1] = w[1]; n.w[2] = w[2];
+}
+__device__ __forceinline__ bool nm_pfx(const NameW &n, const Lit &l) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int cnt = l.len - 8 * k;
+    if (cnt <= 0) continue;
+    const uint64_t m = cnt >= 8 ? ~0ull : (~0ull >> (8 * (8 - cnt)));
+    ok = ok && ((n.w[k] & m) == l.w[k]);
+  }
+  return ok;
+}
+__device__ __forceinline__ unsigned nm_byte(const NameW &n, int i) { return (unsigned)(n.w[i >> 3] >> (8 * (i & 7))) & 0xffu; }
+__device__ __forceinline__ bool nm_eq(const NameW &n, const Lit &l) { return nm_pfx(n, l) && nm_byte(n, l.len) == 0; }
+__device__ __forceinline__ bool nm_is(const NameW &n, const Lit &l) {  // "base" or "base.*"
+  const unsigned c = nm_byte(n, l.len);
+  return nm_pfx(n, l) && (c == 0 || c == '.');
+}
+#define LB2_L(s) lit(s)
+
 // R1: BFD marks these non-alloc names SEC_DEBUGGING; strip removes them.
-__device__ bool is_debug_name(const char *n) {
-  return d_prefix(n, ".debug") || d_prefix(n, ".zdebug") || d_prefix(n, ".gnu.debuglto_.debug_") ||
-         d_prefix(n, ".gnu.linkonce.wi.") || d_prefix(n, ".line") || d_prefix(n, ".stab") || d_streq(n, ".gdb_index");
+__device__ __forceinline__ bool is_debug_name(const NameW &n) {
+  return nm_pfx(n, LB2_L(".debug")) || nm_pfx(n, LB2_L(".zdebug")) || nm_pfx(n, LB2_L(".gnu.debuglto_.debug_")) ||
+         nm_pfx(n, LB2_L(".gnu.linkonce.wi.")) || nm_pfx(n, LB2_L(".line")) || nm_pfx(n, LB2_L(".stab")) || nm_eq(n, LB2_L(".gdb_index"));
 }
 
 // ---- conservative input gate ------------------------------------------------------------------
@@ -131,71 +188,41 @@ __device__ bool is_debug_name(const char *n) {
 // looking up .dynstr/.dynsym, LMA from p_paddr ...).  Files written by ld, gold, lld, patchelf or
 // objcopy already hold BFD's values; anything else is reported LB2_ST_UNSUPPORTED_LAYOUT (-> host
 // strip) rather than guessed at.  Mirrors the gate of the test oracle; found by structure fuzzing.
-__device__ bool name_is(const char *n, const char *base) {  // "base" or "base.*"
-  int l = 0;
-  for (; base[l]; l++) if (n[l] != base[l]) return false;
-  return n[l] == 0 || n[l] == '.';
-}
-__device__ int expected_type_by_name(const char *n) {  // bfd/elf.c special_sections_*; -1: not a special name
-  if (n[0] != '.') return -1;
-  switch (n[1]) {  // one group of literals per second character keeps this to a handful of compares
-    case 'b': if (name_is(n, ".bss")) return SHT_NOBITS; break;
-    case 'c': if (d_streq(n, ".comment")) return SHT_PROGBITS; break;
-    case 'd':
-      if (name_is(n, ".data") || name_is(n, ".data1") || d_prefix(n, ".debug")) return SHT_PROGBITS;
-      if (d_streq(n, ".dynamic")) return SHT_DYNAMIC;
-      if (d_streq(n, ".dynstr")) return SHT_STRTAB;
-      if (d_streq(n, ".dynsym")) return SHT_DYNSYM;
-      break;
-    case 'f':
-      if (d_streq(n, ".fini")) return SHT_PROGBITS;
-      if (name_is(n, ".fini_array")) return SHT_FINI_ARRAY;
-      break;
-    case 'g':
-      if (d_streq(n, ".got")) return SHT_PROGBITS;
-      if (n[2] == 'n' && n[3] == 'u' && n[4] == '.') {
-        if (d_streq(n, ".gnu.version")) return (int)SHT_GNU_VERSYM;
-        if (d_streq(n, ".gnu.version_d")) return (int)SHT_GNU_VERDEF;
-        if (d_streq(n, ".gnu.version_r")) return (int)SHT_GNU_VERNEED;
-        if (d_streq(n, ".gnu.hash")) return (int)SHT_GNU_HASH;
-        if (d_prefix(n, ".gnu.linkonce.b")) return SHT_NOBITS;
-        if (d_prefix(n, ".gnu.linkonce.wi.")) return SHT_PROGBITS;
-      }
-      break;
-    case 'h': if (d_streq(n, ".hash")) return SHT_HASH; break;
-    case 'i':
-      if (d_streq(n, ".init") || d_streq(n, ".interp")) return SHT_PROGBITS;
-      if (name_is(n, ".init_array")) return SHT_INIT_ARRAY;
-      break;
-    case 'l':
-      if (d_prefix(n, ".line") || name_is(n, ".ldata") || name_is(n, ".lrodata")) return SHT_PROGBITS;
-      if (name_is(n, ".lbss")) return SHT_NOBITS;
-      break;
-    case 'n':
-      if (d_prefix(n, ".note")) return SHT_NOTE;
-      if (name_is(n, ".noinit")) return SHT_NOBITS;
-      break;
-    case 'p':
-      if (d_streq(n, ".plt") || name_is(n, ".persistent")) return SHT_PROGBITS;
-      if (name_is(n, ".preinit_array")) return SHT_PREINIT_ARRAY;
-      break;
-    case 'r':
-      if (name_is(n, ".rodata") || name_is(n, ".rodata1")) return SHT_PROGBITS;
-      if (d_prefix(n, ".rela")) return SHT_RELA;
-      if (name_is(n, ".rel")) return SHT_REL;
-      break;
-    case 's':
-      if (name_is(n, ".sbss")) return SHT_NOBITS;
-      if (name_is(n, ".sdata")) return SHT_PROGBITS;
-      if (d_streq(n, ".strtab") || d_streq(n, ".shstrtab")) return SHT_STRTAB;
-      if (d_streq(n, ".symtab")) return SHT_SYMTAB;
-      break;
-    case 't':
-      if (name_is(n, ".tbss")) return SHT_NOBITS;
-      if (name_is(n, ".tdata") || name_is(n, ".text")) return SHT_PROGBITS;
-      break;
-    default: break;
-  }
+__device__ __forceinline__ int expected_type_by_name(const NameW &n) {  // bfd/elf.c special_sections_*; -1: not a special name
+  // (rules for different second characters exclude each other; inside one letter the order is BFD's)
+  if (nm_is(n, LB2_L(".bss"))) return SHT_NOBITS;
+  if (nm_eq(n, LB2_L(".comment"))) return SHT_PROGBITS;
+  if (nm_is(n, LB2_L(".data")) || nm_is(n, LB2_L(".data1")) || nm_pfx(n, LB2_L(".debug"))) return SHT_PROGBITS;
+  if (nm_eq(n, LB2_L(".dynamic"))) return SHT_DYNAMIC;
+  if (nm_eq(n, LB2_L(".dynstr"))) return SHT_STRTAB;
+  if (nm_eq(n, LB2_L(".dynsym"))) return SHT_DYNSYM;
+  if (nm_eq(n, LB2_L(".fini"))) return SHT_PROGBITS;
+  if (nm_is(n, LB2_L(".fini_array"))) return SHT_FINI_ARRAY;
+  if (nm_eq(n, LB2_L(".got"))) return SHT_PROGBITS;
+  if (nm_eq(n, LB2_L(".gnu.version"))) return (int)SHT_GNU_VERSYM;
+  if (nm_eq(n, LB2_L(".gnu.version_d"))) return (int)SHT_GNU_VERDEF;
+  if (nm_eq(n, LB2_L(".gnu.version_r"))) return (int)SHT_GNU_VERNEED;
+  if (nm_eq(n, LB2_L(".gnu.hash"))) return (int)SHT_GNU_HASH;
+  if (nm_pfx(n, LB2_L(".gnu.linkonce.b"))) return SHT_NOBITS;
+  if (nm_pfx(n, LB2_L(".gnu.linkonce.wi."))) return SHT_PROGBITS;
+  if (nm_eq(n, LB2_L(".hash"))) return SHT_HASH;
+  if (nm_eq(n, LB2_L(".init")) || nm_eq(n, LB2_L(".interp"))) return SHT_PROGBITS;
+  if (nm_is(n, LB2_L(".init_array"))) return SHT_INIT_ARRAY;
+  if (nm_pfx(n, LB2_L(".line")) || nm_is(n, LB2_L(".ldata")) || nm_is(n, LB2_L(".lrodata"))) return SHT_PROGBITS;
+  if (nm_is(n, LB2_L(".lbss"))) return SHT_NOBITS;
+  if (nm_pfx(n, LB2_L(".note"))) return SHT_NOTE;
+  if (nm_is(n, LB2_L(".noinit"))) return SHT_NOBITS;
+  if (nm_eq(n, LB2_L(".plt")) || nm_is(n, LB2_L(".persistent"))) return SHT_PROGBITS;
+  if (nm_is(n, LB2_L(".preinit_array"))) return SHT_PREINIT_ARRAY;
+  if (nm_is(n, LB2_L(".rodata")) || nm_is(n, LB2_L(".rodata1"))) return SHT_PROGBITS;
+  if (nm_pfx(n, LB2_L(".rela"))) return SHT_RELA;
+  if (nm_is(n, LB2_L(".rel"))) return SHT_REL;
+  if (nm_is(n, LB2_L(".sbss"))) return SHT_NOBITS;
+  if (nm_is(n, LB2_L(".sdata"))) return SHT_PROGBITS;
+  if (nm_eq(n, LB2_L(".strtab")) || nm_eq(n, LB2_L(".shstrtab"))) return SHT_STRTAB;
+  if (nm_eq(n, LB2_L(".symtab"))) return SHT_SYMTAB;
+  if (nm_is(n, LB2_L(".tbss"))) return SHT_NOBITS;
+  if (nm_is(n, LB2_L(".tdata")) || nm_is(n, LB2_L(".text"))) return SHT_PROGBITS;
   return -1;
 }
 __device__ bool type_is_known(uint32_t t) {
@@ -246,15 +273,22 @@ __device__ int strrev_cmp(const char *a, int la, const char *b, int lb) {
 }
 
 // ---------------------------------------------------------------- R9: objcopy merge_gnu_build_notes
-#ifdef LB2_HOST_EMULATION
-#define LB2_PREFETCH_L1(p) do { } while (0)
-#else
-#define LB2_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
-#endif
-// note bytes are read straight from the arena (through L1); a hostile sh_offset may be unaligned
-__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) {
-  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) return __ldg(reinterpret_cast<const uint32_t *>(p));
-  return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+// note records are read from the shared-memory copy of the section; offsets stay multiples of 4
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+// Warp-cooperative global->shared copy (16-byte vectors when the source allows it, bytes otherwise).
+__device__ __forceinline__ void warp_g2s(void *dst_s, const uint8_t *src_g, uint32_t nbytes, int lane) {
+  uint8_t *d = static_cast<uint8_t *>(dst_s);
+  if ((reinterpret_cast<uintptr_t>(src_g) & 15) == 0) {
+    const uint32_t nv = nbytes >> 4;
+    for (uint32_t i = lane; i < nv; i += 32) reinterpret_cast<uint4 *>(d)[i] = __ldg(reinterpret_cast<const uint4 *>(src_g) + i);
+    for (uint32_t i = (nv << 4) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  } else if ((reinterpret_cast<uintptr_t>(src_g) & 3) == 0) {
+    const uint32_t nv = nbytes >> 2;
+    for (uint32_t i = lane; i < nv; i += 32) reinterpret_cast<uint32_t *>(d)[i] = __ldg(reinterpret_cast<const uint32_t *>(src_g) + i);
+    for (uint32_t i = (nv << 2) + lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  } else {
+    for (uint32_t i = lane; i < nbytes; i += 32) d[i] = __ldg(src_g + i);
+  }
 }
 __device__ __forceinline__ void wr32(uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; }
 __device__ __forceinline__ void wr64(uint8_t *p, uint64_t v) { wr32(p, (uint32_t)v); wr32(p + 4, (uint32_t)(v >> 32)); }
@@ -268,7 +302,7 @@ __device__ __forceinline__ int cmp_note_names(const PlanSmem &sm, const uint8_t 
   if (m >= 8) {
     if (ka != kb) return ka < kb ? -1 : 1;
     const uint8_t *n1 = nbuf + a.off + 12 + 3, *n2 = nbuf + b.off + 12 + 3;
-    for (int i = 8; i < m; i++) { const int x = __ldg(n1 + i), y = __ldg(n2 + i); if (x != y) return x - y; }
+    for (int i = 8; i < m; i++) { const int x = n1[i], y = n2[i]; if (x != y) return x - y; }
     return 0;
   }
   const uint64_t x = ka >> (8 * (8 - m)), y = kb >> (8 * (8 - m));
@@ -293,17 +327,6 @@ __device__ __forceinline__ int cmp_by_attr(const PlanSmem &sm, const uint8_t *nb
   if (a.type != 0x100 && b.type == 0x100) return 1;
   return 0;
 }
-// second sort: by address range (objcopy.c sort_gnu_build_notes)
-__device__ __forceinline__ int cmp_by_addr(const DNote &a, const DNote &b) {
-  if (a.type == 0x100 && b.type != 0x100) return -1;  // OPEN notes first
-  if (a.type != 0x100 && b.type == 0x100) return 1;
-  if (a.start < b.start) return -1;
-  if (a.start > b.start) return 1;
-  if (a.end > b.end) return -1;                        // larger ranges first
-  if (a.end < b.end) return 1;
-  return 0;  // ties keep the order of the first sort (stable merge)
-}
-
 // objcopy sorts the notes with libc qsort(); its first comparator is not antisymmetric for nested
 // ranges, so the result depends on the exact comparison sequence.  This image's glibc 2.39 qsort
 // is the classic top-down merge sort (msort.c: n1 = n / 2, sort both halves, merge taking the left
@@ -321,7 +344,7 @@ __device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int
   }
   *lo = l; *hi = h;
 }
-template <bool SECOND, bool FAST>
+template <bool FAST>
 __device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int lane) {
   const DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
@@ -340,7 +363,7 @@ __device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int l
       DNote a = notes[pa], b = notes[pb];
       DNote a_n = notes[pa_n], b_n = notes[pb_n];
       while (true) {
-        const int c = SECOND ? cmp_by_addr(a, b) : cmp_by_attr<FAST>(sm, nbuf, a, pa, b, pb);
+        const int c = cmp_by_attr<FAST>(sm, nbuf, a, pa, b, pb);
         if (c <= 0) {
           tmp[w++] = pa; i++;
           if (--r1 == 0) break;
@@ -360,6 +383,56 @@ __device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int l
   }
 }
 
+// Wherever the comparator IS a strict weak order, glibc's merge sort is simply a stable sort and the result
+// can be written down directly: position = number of elements that sort before (ties by current position).
+// All pairs are independent -- no sequential merge steps at all.
+//   FIRST = false: objcopy.c sort_gnu_build_notes -- OPEN notes first, start ascending, larger ranges first.
+//                  A lexicographic order: always consistent.
+//   FIRST = true : objcopy.c compare_gnu_build_notes -- by attribute name, then by range.  Within one name it
+//                  equals (start, end, OPEN first) exactly when no note starts inside an earlier-starting note
+//                  of the same name without also ending behind it, and no note has start > end (see the case
+//                  analysis in DESIGN.md).  The pass checks that while it counts; if it fails, nothing has been
+//                  written and the caller runs the restated merge sort instead.
+template <bool FIRST>
+__device__ bool warp_ranksort_notes(PlanSmem &sm, int n, int lane) {
+  const DNote *__restrict__ notes = sm.u.n.notes;
+  uint16_t *__restrict__ perm = sm.u.n.perm;
+  uint16_t *__restrict__ tmp = sm.u.n.tmp;
+  int viol = 0;
+  for (int p0 = 0; p0 < n; p0 += 32) {
+    const int p = p0 + lane;
+    if (p < n) {
+      const uint16_t ip = perm[p];
+      const DNote a = notes[ip];
+      const bool a_open = a.type == 0x100;
+      if (FIRST && a.start > a.end) viol = 1;
+      int r = 0;
+#pragma unroll 2
+      for (int q = 0; q < n; q++) {
+        const DNote b = notes[perm[q]];
+        const bool b_open = b.type == 0x100;
+        int c;  // sign of compare(b, a)
+        if (FIRST) {
+          if (b.nrank != a.nrank) c = b.nrank < a.nrank ? -1 : 1;
+          else {
+            if (b.start < a.start && a.start <= b.end && a.end <= b.end) viol = 1;
+            c = b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end < a.end ? -1 : 1) : (b_open == a_open ? 0 : (b_open ? -1 : 1));
+          }
+        } else {
+          c = b_open != a_open ? (b_open ? -1 : 1) : b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end > a.end ? -1 : 1) : 0;
+        }
+        r += (c < 0) || (c == 0 && q < p);
+      }
+      tmp[r] = ip;
+    }
+    if (FIRST && __ballot_sync(0xffffffffu, viol)) return false;   // not an order: stop after this round of 32
+  }
+  __syncwarp();
+  for (int p = lane; p < n; p += 32) perm[p] = tmp[p];
+  __syncwarp();
+  return true;
+}
+
 // 64-bit value of the nearest lane at or below `lane` whose bit is set in `mask`, else `carry`
 __device__ __forceinline__ uint64_t last_set_value(unsigned mask, uint64_t v, uint64_t carry, int lane) {
   const unsigned m = mask & (0xffffffffu >> (31 - lane));
@@ -368,12 +441,18 @@ __device__ __forceinline__ uint64_t last_set_value(unsigned mask, uint64_t v, ui
   return m ? got : carry;
 }
 
+#ifdef LB2_HOST_EMULATION   // the CPU emulator reports which sort path a file took, so the tests can insist both are covered
+static int lb2_path_counts[3];   // [0] rank sort, [1] merge sort with name ranks, [2] merge sort with full name compares
+#define LB2_COUNT(k) do { if (lane == 0) __atomic_fetch_add(&lb2_path_counts[k], 1, __ATOMIC_RELAXED); } while (0)
+#else
+#define LB2_COUNT(k) do { } while (0)
+#endif
 #ifdef LB2_PLAN_TIMING
 #define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
 #else
 #define LB2_NT(k) do { } while (0)
 #endif
-// Merges the `size` bytes of notes at nbuf (arena) and writes the result to `out` (global scratch).
+// Merges the `size` bytes of notes at nbuf (the shared-memory copy of the section) and writes the result to `out` (global scratch).
 // Returns the new size; *err: 1 = objcopy would report corrupt notes, 2 = more notes than the workspace
 // holds.  Warp-collective (one warp).
 __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_t size, uint8_t *out, int *err, int lane) {
@@ -385,7 +464,6 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
   long long nt_[10];
 #endif
   LB2_NT(0);
-  for (uint32_t i = (uint32_t)lane * 128; i < size; i += 32 * 128) LB2_PREFETCH_L1(nbuf + i);
   // 1. lane 0 walks the variable-length records (three words each) and records where every note starts
   int n = 0, e1 = 0;
   if (lane == 0) {
@@ -423,11 +501,11 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       d.namesz = (uint16_t)namesz;
       d.type = (uint16_t)type;
       d.ver = 0; d.pad = 0; d.nrank = 0;
-      const uint8_t c0 = __ldg(nm), c1 = __ldg(nm + 1), c2 = __ldg(nm + 2);
+      const uint8_t c0 = nm[0], c1 = nm[1], c2 = nm[2];
       if (c0 == '$' && c1 == 1 && c2 == '1') v1 = 1;
-      else if (namesz > 4 && c0 == 'G' && c1 == 'A' && c2 == '$' && __ldg(nm + 3) == 1) {
+      else if (namesz > 4 && c0 == 'G' && c1 == 'A' && c2 == '$' && nm[3] == 1) {
         d.ver = 1;
-        const uint8_t c4 = __ldg(nm + 4);
+        const uint8_t c4 = nm[4];
         if (c4 == '2') v2 = 1;
         else if (c4 == '3') v3 = 1;
         else { bad = 1; continue; }
@@ -441,11 +519,11 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       if (start > end) start = end;
       d.start = start;   // raw; ranges inherited from earlier notes are filled in by step 3
       d.end = end;
-      if (__ldg(nm + namesz - 1) != 0) { bad = 1; continue; }
+      if (nm[namesz - 1] != 0) { bad = 1; continue; }
       uint64_t key = 0;
       uint32_t hsh = 2166136261u;
       for (int q = 0; q < (int)namesz; q++) {
-        const uint8_t ch = __ldg(nm + q);
+        const uint8_t ch = nm[q];
         hsh = (hsh ^ ch) * 16777619u;
         if (q >= 3 && q < 11) key = (key << 8) | ch;
       }
@@ -460,7 +538,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
     if (!a1 && !a2 && !a3) a3 = true;  // "version note missing - assuming version 3"
     if ((a1 && a2) || (a1 && a3) || (a2 && a3)) { *err = 1; return size; }
     if (!a3 || size < 12) {            // only v3 notes are merged
-      for (uint32_t i = lane; i < size; i += 32) out[i] = __ldg(nbuf + i);
+      for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
       return size;
     }
   }
@@ -496,7 +574,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       if (notes[j].tag != tag) continue;
       const uint8_t *om = nbuf + notes[j].off + 12;
       bool same = true;
-      for (int q = 0; q < (int)d.namesz; q++) if (__ldg(om + q) != __ldg(nm + q)) { same = false; break; }
+      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
       if (same) { cls = j; break; }
     }
     d.cls = (uint16_t)cls;
@@ -523,8 +601,9 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
   for (int i = lane; i < n; i += 32) if (notes[i].cls != i) notes[i].nrank = notes[notes[i].cls].nrank;
   __syncwarp();
   LB2_NT(2);
-  if (amb) warp_msort_notes<false, false>(sm, nbuf, n, lane);   // restated glibc merge sort, level by level across lanes
-  else warp_msort_notes<false, true>(sm, nbuf, n, lane);
+  if (amb) { LB2_COUNT(2); warp_msort_notes<false>(sm, nbuf, n, lane); }   // restated glibc merge sort, level by level across lanes
+  else if (warp_ranksort_notes<true>(sm, n, lane)) LB2_COUNT(0);
+  else { LB2_COUNT(1); warp_msort_notes<true>(sm, nbuf, n, lane); }
   LB2_NT(3);
   // 5. objcopy's merge pass: every note looks back over the SURVIVING notes of the same attribute (at most 17).
   //    The survivors so far are kept as a stack in tmp[], so deleted notes cost nothing to skip.
@@ -561,7 +640,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
   }
   __syncwarp();
   LB2_NT(4);
-  warp_msort_notes<true, true>(sm, nbuf, n, lane);
+  warp_ranksort_notes<false>(sm, n, lane);
   LB2_NT(5);
   // 6. output offsets and range elision: a surviving note drops its description when its range equals the
   //    previous survivor's.  Ballot + shuffle scan, 32 sorted positions a round.
@@ -597,7 +676,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
   }
   __syncwarp();
   if (newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
-    for (uint32_t i = lane; i < size; i += 32) out[i] = __ldg(nbuf + i);
+    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
     __syncwarp();
     return size;
   }
@@ -612,7 +691,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
     wr32(o + 4, elide ? 0u : 16u);
     wr32(o + 8, pn.type);
     const uint8_t *nm = nbuf + pn.off + 12;
-    for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? __ldg(nm + q) : 0;
+    for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? nm[q] : 0;
     if (!elide) { wr64(o + 12 + padded, pn.start); wr64(o + 20 + padded, pn.end); }
   }
   __syncwarp();
@@ -733,6 +812,21 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     if (err_uns) sm.err_uns = 1;
   }
   if (tid >= 96 && tid < 104 && reinterpret_cast<const uint64_t *>(&sm.sh[0])[tid - 96] != 0) sm.err_uns = 1;  // section 0: the all-zero NULL header
+  NameW nw;
+  nw.w[0] = nw.w[1] = nw.w[2] = 0;
+  bool name_ok = false;
+  if (tid < shnum) {  // C0: every section's name -> packed words, hash, length, and whether it is .dynstr / .dynsym
+    const Shdr &h = sm.sh[tid];
+    uint8_t kind = 0;
+    if (h.sh_name < strsz) {
+      name_ok = true;
+      name_words(sm.names + h.sh_name, nw);
+      { int ln; sm.name_hash[tid] = d_hash(sm.names + h.sh_name, &ln); sm.name_len[tid] = (uint16_t)ln; }
+      kind = nm_eq(nw, LB2_L(".dynstr")) ? 1 : (nm_eq(nw, LB2_L(".dynsym")) ? 2 : 0);
+    }
+    sm.name_kind[tid] = kind;
+  }
+  __syncthreads();
   if (tid < 64) {
     const int i = tid;
     int is_keep = 0, is_alloc = 0, is_nobits = 0;
@@ -741,18 +835,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       Shdr &h = sm.sh[i];
       sm.seg[i] = -1; sm.new_size[i] = h.sh_size; sm.new_off[i] = 0;
       sm.src_addr[i] = reinterpret_cast<uint64_t>(in) + h.sh_offset;
-      if (h.sh_name >= strsz) err_mal = 1;
+      if (!name_ok) err_mal = 1;
       else if (h.sh_type != SHT_NOBITS && h.sh_type != SHT_NULL && (h.sh_offset > n || h.sh_size > n - h.sh_offset)) err_mal = 1;
       else {
-        { int ln; sm.name_hash[i] = d_hash(sm.names + h.sh_name, &ln); sm.name_len[i] = (uint16_t)ln; }
         if (i == 0) is_keep = 1;
         else {
-          const char *nm = sm.names + h.sh_name;
           const bool alloc = (h.sh_flags & SHF_ALLOC) != 0;
           bool drop = false;
           if (h.sh_type == SHT_SYMTAB || h.sh_type == SHT_SYMTAB_SHNDX) drop = true;
           else if (h.sh_type == SHT_STRTAB && !alloc) drop = true;
-          else if (!alloc && is_debug_name(nm)) drop = true;
+          else if (!alloc && is_debug_name(nw)) drop = true;
           if (h.sh_type == SHT_NULL || h.sh_type == SHT_GROUP) err_uns = 1;
           if ((h.sh_type == SHT_DYNSYM || h.sh_type == SHT_SYMTAB || h.sh_type == SHT_RELA) && h.sh_entsize != 24) err_uns = 1;
           if (h.sh_type == SHT_GNU_VERSYM && h.sh_entsize != 2) err_uns = 1;
@@ -761,7 +853,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
           if (!alloc && (h.sh_type == SHT_REL || h.sh_type == SHT_RELA)) err_uns = 1;
           {  // ---- gate (see expected_type_by_name)
             const uint64_t ALLOWED = 0x1 | 0x2 | 0x4 | 0x10 | 0x20 | 0x40 | 0x400 | 0x800 | 0x200000 | 0x10000000;
-            const int want = expected_type_by_name(nm);
+            const int want = expected_type_by_name(nw);
             if (h.sh_flags & ~ALLOWED) err_uns = 1;
             if (!type_is_known(h.sh_type)) err_uns = 1;
             if (h.sh_type == SHT_NOBITS && !alloc) err_uns = 1;
@@ -770,18 +862,18 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
             if (h.sh_link >= (uint32_t)shnum) err_uns = 1;
             else {
               const Shdr &lk = sm.sh[h.sh_link];
-              const char *lname = lk.sh_name < strsz ? sm.names + lk.sh_name : "";
+              const int lkind = sm.name_kind[h.sh_link];   // 1 .dynstr, 2 .dynsym, 0 anything else (or a name out of range)
               switch (h.sh_type) {
                 case SHT_DYNSYM: case SHT_DYNAMIC: case SHT_GNU_VERDEF: case SHT_GNU_VERNEED:  // BFD: sh_link := index of .dynstr
-                  if (h.sh_link == 0 || !d_streq(lname, ".dynstr")) err_uns = 1;
+                  if (h.sh_link == 0 || lkind != 1) err_uns = 1;
                   if (h.sh_type == SHT_DYNAMIC && h.sh_info != 0) err_uns = 1;
                   if (h.sh_type == SHT_DYNSYM && (h.sh_size % 24 != 0 || h.sh_info > h.sh_size / 24)) err_uns = 1;
                   break;
                 case SHT_HASH: case SHT_GNU_HASH: case SHT_GNU_VERSYM:                         // BFD: sh_link := index of .dynsym
-                  if (h.sh_link == 0 || !d_streq(lname, ".dynsym") || h.sh_info != 0) err_uns = 1;
+                  if (h.sh_link == 0 || lkind != 2 || h.sh_info != 0) err_uns = 1;
                   break;
                 case SHT_RELA: case SHT_REL:
-                  if (h.sh_link != 0 && !d_streq(lname, ".dynsym")) err_uns = 1;
+                  if (h.sh_link != 0 && lkind != 2) err_uns = 1;
                   if (h.sh_info >= (uint32_t)shnum) err_uns = 1;
                   break;
                 case SHT_SYMTAB:  // dropped, but BFD reads it first and refuses a broken one
@@ -1079,7 +1171,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
         if (h.sh_size > (uint64_t)MAX_NOTE_BYTES || scr_used + h.sh_size > MAX_NOTE_BYTES) { nfail = ST_PLANNER_LIMIT; break; }
         int err = 0;
         uint8_t *dst = scr + SCR_NOTES + scr_used;
-        const uint32_t ns = merge_build_notes(sm, in + h.sh_offset, (uint32_t)h.sh_size, dst, &err, lane);
+        warp_g2s(sm.u.n.buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
+        __syncwarp();
+        const uint32_t ns = merge_build_notes(sm, sm.u.n.buf, (uint32_t)h.sh_size, dst, &err, lane);
         if (err) { nfail = err == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES; break; }
         if (lane == 0) {
           sm.new_size[i] = ns;
@@ -1293,7 +1387,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
         // assign_section_numbers(): an allocated reloc section without a symbol table gets .dynsym
         for (int q = 1; q < nk; q++) {
           const int oi = sm.order[q];
-          if (sm.name_len[oi] == 7 && d_streq(sm.names + sm.sh[oi].sh_name, ".dynsym")) { h.sh_link = (uint32_t)q; break; }
+          if (sm.name_kind[oi] == 2) { h.sh_link = (uint32_t)q; break; }
         }
       }
       if (h.sh_type == SHT_REL || h.sh_type == SHT_RELA) {
@@ -1389,6 +1483,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     };
     ExtWork &x = sm.u.x;
     int ne = 0, bad = 0;
+    unsigned long long big0 = 0, big1 = 0, big2 = 0;   // extents with > 64 tiles (bit = extent index, MAX_EXT = 140)
+    auto mark_big = [&](int at) { if (at < 64) big0 |= 1ull << at; else if (at < 128) big1 |= 1ull << (at - 64); else big2 |= 1ull << (at - 128); };
     unsigned long long copy_bytes = 0;
     uint32_t running = 0;
     for (int q0 = 0; q0 < total_pieces; q0 += 32) {
@@ -1413,8 +1509,13 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       if (valid) {
         int at = ne + lane + __popc(gm & ((1u << lane) - 1));
         uint32_t t0 = running + inc - (cnt_gap + cnt);
-        if (gap) { x.src[at] = 0; x.dst[at] = prev_end; x.len[at] = dst - prev_end; x.tiles[at] = t0; t0 += cnt_gap; at++; }  // file hole
+        if (gap) {  // file hole
+          x.src[at] = 0; x.dst[at] = prev_end; x.len[at] = dst - prev_end; x.tiles[at] = t0; t0 += cnt_gap;
+          if (cnt_gap > 64) mark_big(at);
+          at++;
+        }
         x.src[at] = src; x.dst[at] = dst; x.len[at] = len; x.tiles[at] = t0;
+        if (cnt > 64) mark_big(at);
         copy_bytes += len;
       }
       running += __shfl_sync(0xffffffffu, inc, 31);
@@ -1422,10 +1523,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       ne += nvalid + __popc(gm);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) copy_bytes += __shfl_xor_sync(0xffffffffu, copy_bytes, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      copy_bytes += __shfl_xor_sync(0xffffffffu, copy_bytes, o);
+      big0 |= __shfl_xor_sync(0xffffffffu, big0, o);
+      big1 |= __shfl_xor_sync(0xffffffffu, big1, o);
+      big2 |= __shfl_xor_sync(0xffffffffu, big2, o);
+    }
     const bool any_bad = __ballot_sync(0xffffffffu, bad) != 0;
     if (lane == 0) {
-      sm.n_ext = ne; sm.copy_bytes = copy_bytes; sm.n_tiles = running;
+      sm.n_ext = ne; sm.copy_bytes = copy_bytes; sm.n_tiles = running; sm.big_ext[0] = big0; sm.big_ext[1] = big1; sm.big_ext[2] = big2;
       if (any_bad) sm.fail = ST_UNSUPPORTED_LAYOUT;
       else sm.tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);   // one atomicAdd per file reserves the range
     }
@@ -1441,16 +1547,13 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     if (tid == 0) { a.ctr->overflow = 1; a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; }
     return;
   }
-  for (int e = 0; e < n_ext; e++) {
+  auto emit_tiles = [&](int e, uint32_t k, const uint32_t step) {
     const uint64_t d = sm.u.x.dst[e], l = sm.u.x.len[e], s = sm.u.x.src[e];
-    if (l == 0) continue;
+    if (l == 0) return;
     const uint64_t t0 = d / TILE_BYTES;
     const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - t0 + 1);
     Tile *out = a.tiles + tile_base + sm.u.x.tiles[e];
-    uint32_t k, step;
-    if (cnt > 64) { k = tid; step = PLAN_THREADS; }
-    else if ((e & 3) == warp) { k = lane; step = 32; }
-    else continue;
+#pragma unroll 4
     for (; k < cnt; k += step) {
       uint64_t b = (t0 + k) * TILE_BYTES, en = b + TILE_BYTES;
       if (b < d) b = d;
@@ -1462,7 +1565,17 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       t.file = f;
       out[k] = t;
     }
+  };
+  // small extents: one per warp (a thread only looks at its warp's share of the list); the few extents
+  // with hundreds of tiles were set aside by phase L and are written by the whole CTA
+  const unsigned long long big0 = sm.big_ext[0], big1 = sm.big_ext[1], big2 = sm.big_ext[2];
+  for (int e = warp; e < n_ext; e += PLAN_THREADS / 32) {
+    const bool big = ((e < 64 ? big0 >> e : (e < 128 ? big1 >> (e - 64) : big2 >> (e - 128))) & 1) != 0;
+    if (!big) emit_tiles(e, lane, 32);
   }
+  for (unsigned long long m = big0; m; m &= m - 1) emit_tiles(__ffsll((long long)m) - 1, tid, PLAN_THREADS);
+  for (unsigned long long m = big1; m; m &= m - 1) emit_tiles(64 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
+  for (unsigned long long m = big2; m; m &= m - 1) emit_tiles(128 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
   LB2_T(9);
 #ifdef LB2_PLAN_TIMING
   if (tid == 0 && f == 0) {

@@ -26,6 +26,12 @@ class Emu:
         self.lib.lb2emu_strip.restype = ctypes.c_int
         self.lib.lb2emu_free.argtypes = [ctypes.c_void_p]
 
+    def path_counts(self):
+        """[rank-sorted, merge-sorted by name rank, merge-sorted with full name compares] note sections so far"""
+        out = (ctypes.c_int * 3)()
+        self.lib.lb2emu_path_counts(out)
+        return list(out)
+
     def strip(self, data, no_merge=False):
         """-> (status, bytes|None): status as the device planner reports it (0 ok, >0 class, <0 malformed,
         -1000/-1001: the emitted tiles do not tile the output exactly)"""

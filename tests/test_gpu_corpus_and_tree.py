@@ -23,12 +23,16 @@ pytestmark = pytest.mark.gpu
 
 def test_random_note_sections_gpu(gpu_ctx, oracle, variants, fixture_dir):
     from lambdipy_b200 import strip as S
-    from test_oracle_vs_gnu_strip import _random_notes
+    from test_oracle_vs_gnu_strip import _random_notes, _staircase_notes
     rng = random.Random(77)
     blobs = []
     for case in range(60):
         p = os.path.join(fixture_dir, "gpu_rnd_notes_%d.so" % case)
         assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([3, 8, 20, 60, 150])))
+        blobs.append(open(p, "rb").read())
+    for case in range(60):   # orders that ARE orders: the planner's rank-sort path (and its fallback when one range nests)
+        p = os.path.join(fixture_dir, "gpu_stair_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _staircase_notes(rng, rng.choice([4, 12, 40, 90, 130])))
         blobs.append(open(p, "rb").read())
     outs, status, _ = S.strip_buffers(gpu_ctx, blobs)
     for i, (b, o, st) in enumerate(zip(blobs, outs, status)):

@@ -84,6 +84,44 @@ def _random_notes(rng, n):
     return notes
 
 
+def _staircase_notes(rng, n):
+    """annobin-like sections: per attribute name, ranges whose starts AND ends ascend (disjoint, touching, closer than 16
+    bytes, overlapping staircase-wise), equal starts, duplicates, notes without a range -- within one name the sort
+    comparator is then a proper order (the device planner's rank-sort path); now and then one nested range breaks it."""
+    O, Fn = 0x100, 0x101
+    names = [b"GA*\x02\x03\x00", b"GA*\x07\x02\x00", b"GA*FORTIFY\x00\x02\x00", b"GA+stack_clash\x00", b"GA!\x08\x00", b"GA*GOW\x00\x2a\x05\x02\x00"]
+    notes = [(F.GA_VERSION, O, (0x1000, 0x1000 + rng.randrange(1, 0x400)))]
+    per_name = max(1, n // len(names))
+    for nm in rng.sample(names, rng.randrange(1, len(names) + 1)):
+        s, e = 0x1000 + rng.randrange(0, 64), 0
+        for _ in range(per_name):
+            e = max(e + rng.choice([1, 3, 0x20]), s + rng.choice([1, 8, 0x40, 0x200]))
+            typ = O if rng.random() < 0.8 else Fn
+            notes.append((nm, typ, (s, e) if rng.random() < 0.9 else None))
+            if rng.random() < 0.15:
+                notes.append(notes[-1])
+            if rng.random() < 0.1:
+                notes.append((nm, typ, (s, e + rng.choice([1, 0x10]))))      # same start, later end
+            s = rng.choice([e, e + 1, e + 8, e + 15, e + 16, e + 17, e + 0x100, max(s + 1, e - rng.choice([1, 4]))])
+    if rng.random() < 0.25 and len(notes) > 3:
+        nm, typ, r = notes[rng.randrange(1, len(notes))]
+        if r:
+            notes.insert(rng.randrange(1, len(notes)), (nm, typ, (r[0] + 1, max(r[0] + 1, r[1] - 1))))  # nested: the order stops being one
+    rng.shuffle(notes[1:]) if rng.random() < 0.3 else None
+    return notes
+
+
+def test_staircase_note_sections(oracle, variants, fixture_dir, tmp_path):
+    rng = random.Random(424242)
+    for case in range(40):
+        notes = _staircase_notes(rng, rng.choice([4, 12, 40, 90, 200]))
+        p = os.path.join(fixture_dir, "stair_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, notes)
+        data, gnu, rc, out, err = _diff(oracle, p, str(tmp_path))
+        assert gnu is not None, err
+        assert rc == 0 and out == gnu, "staircase note case %d" % case
+
+
 def test_random_note_sections(oracle, variants, fixture_dir, tmp_path):
     """nested, overlapping, adjoining, duplicate and empty ranges over many attribute names: the
     comparator objcopy sorts with is not antisymmetric, the merge-sort sequence matters"""

@@ -57,7 +57,7 @@ def test_variants_notes_edges(emu, oracle, variants, note_files, doctored, no_me
 
 def test_random_notes_and_structure_fuzz(emu, oracle, variants, fixture_dir, tmp_path):
     import sys
-    from test_oracle_vs_gnu_strip import _random_notes
+    from test_oracle_vs_gnu_strip import _random_notes, _staircase_notes
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     import fuzz_vs_gnu as Z
     rng = random.Random(5)
@@ -65,6 +65,14 @@ def test_random_notes_and_structure_fuzz(emu, oracle, variants, fixture_dir, tmp
         p = os.path.join(fixture_dir, "emu_rnd_notes_%d.so" % case)
         assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([3, 8, 20, 60, 150])))
         assert _agree(emu, oracle, _read(p)) == 0
+    c0 = emu.path_counts()
+    assert c0[1] > 10, c0          # random ranges nest: the restated merge sort ran
+    for case in range(40):
+        p = os.path.join(fixture_dir, "emu_stair_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _staircase_notes(rng, rng.choice([4, 12, 40, 90, 130])))
+        assert _agree(emu, oracle, _read(p)) == 0
+    c1 = emu.path_counts()
+    assert c1[0] - c0[0] > 10 and c1[1] - c0[1] > 2, (c0, c1)   # proper orders took the rank sort, the nested ones fell back
     seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
     accepted = 0
     for k in range(300):
