@@ -422,10 +422,10 @@ def real_trees_block(ctx, peak):
 
 # ---------------------------------------------------------------- B200 arm
 def run_b200(a, rank, local_rank, world):
-    # NCCL's INFO lines (communicator, nranks, transport) go to stderr; stdout carries the ONE JSON line
+    # NCCL's own INIT lines (communicator, nranks, transport) stay visible on its default sink (stdout; pointing
+    # NCCL_DEBUG_FILE at /dev/stderr lost them on the GPU box).  The JSON line is the LAST line rank 0 prints.
     os.environ.setdefault("NCCL_DEBUG", os.environ.get("LB2_NCCL_DEBUG", "INFO"))
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
     from lambdipy_b200 import _native as N
@@ -442,8 +442,12 @@ def run_b200(a, rank, local_rank, world):
     n = len(corpus)
     in_span = int(corpus.off[-1])
     free_b, total_b = torch.cuda.mem_get_info()
-    chunked = (2 * in_span + n * 4096 + (1 << 30)) > 0.85 * free_b
-    chunk_bytes = int(a.chunk_gb * (1 << 30)) if chunked else None
+    # The output always streams through the two-slot ring of lb2_strip_device_chunked: a shard whose input + output
+    # exceed HBM (N=1) needs it, and with at least two chunks per step the next batch is already queued while the host
+    # collects the previous one at every N.
+    big = (2 * in_span + n * 4096 + (1 << 30)) > 0.85 * free_b
+    chunk_bytes = int(a.chunk_gb * (1 << 30)) if big else max(in_span // 2 + (64 << 20), 1 << 28)
+    chunked = True
     batch = DeviceBatch.from_corpus(ctx, corpus, chunk_bytes=chunk_bytes)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
@@ -621,7 +625,7 @@ def run_b200(a, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": dict(workload_config(a, world), batches_per_step_rank0=batches_per_step,
-                                                               output_ring="two slots of %.1f GB (input + output exceed HBM)" % (batch.slot_cap / 1e9) if chunked else None),
+                                                               output_ring="two slots of %.1f GB%s" % (batch.slot_cap / 1e9, " (input + output exceed HBM)" if big else "")),
             "totals": {"files": int(n_ok), "unsupported_files": int(n_uns), "in_gb": tot_in / 1e9, "out_gb": tot_out / 1e9,
                        "copied_gb": tot_copy / 1e9, "header_gb": tot_hdr / 1e9},
             "roofline": {"bound": "hbm", "kernel": "lb2_compact_kernel" if os.environ.get("LB2_COMPACT_TMA") == "0" else "lb2_compact_tma_kernel",
@@ -648,12 +652,14 @@ def run_b200(a, rank, local_rank, world):
         assert n_bad == 0, "parity sample failed: %d mismatches" % n_bad
         if world == 1 and not a.no_host_legs:
             line.update(host_legs(a, ctx, corpus, batch, ns, peak))
-        print(json.dumps(line))
     ctx.pinned_free(h_in); ctx.pinned_free(h_out)
     batch.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     return 0
 
 
