@@ -424,8 +424,9 @@ def real_trees_block(ctx, peak):
 def run_b200(a, rank, local_rank, world):
     # NCCL's own INIT lines (communicator, nranks, transport) stay visible on its default sink (stdout; pointing
     # NCCL_DEBUG_FILE at /dev/stderr lost them on the GPU box).  The JSON line is the LAST line rank 0 prints.
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("LB2_NCCL_DEBUG", "INFO"))
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    # (forced, not setdefault: the image exports NCCL_DEBUG=VERSION, which hides the communicator lines)
+    os.environ["NCCL_DEBUG"] = os.environ.get("LB2_NCCL_DEBUG", "INFO")
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("LB2_NCCL_DEBUG_SUBSYS", "INIT")
     import numpy as np
     import torch
     from lambdipy_b200 import _native as N
