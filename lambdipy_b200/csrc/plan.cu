@@ -572,9 +572,13 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
     int cls = i;
     for (int j = 0; j < i; j++) {
       if (notes[j].tag != tag) continue;
-      const uint8_t *om = nbuf + notes[j].off + 12;
+      // confirm the (near certain) match word by word: names start at 4-aligned offsets of the staged section,
+      // namesz is equal (it is part of the tag), bytes behind namesz are masked off in the last word
+      const uint32_t *ow = reinterpret_cast<const uint32_t *>(nbuf + notes[j].off + 12), *mw = reinterpret_cast<const uint32_t *>(nm);
+      const int nw = (int)d.namesz >> 2, rem = (int)d.namesz & 3;
       bool same = true;
-      for (int q = 0; q < (int)d.namesz; q++) if (om[q] != nm[q]) { same = false; break; }
+      for (int q = 0; q < nw; q++) if (ow[q] != mw[q]) { same = false; break; }
+      if (same && rem) same = ((ow[nw] ^ mw[nw]) & (0xffffffffu >> (8 * (4 - rem)))) == 0;
       if (same) { cls = j; break; }
     }
     d.cls = (uint16_t)cls;

@@ -95,6 +95,45 @@ def test_synthetic_corpus_device_resident(gpu_ctx, oracle, tmp_path):
         batch.close()
 
 
+def test_chunked_device_api_equals_one_batch(gpu_ctx, oracle):
+    """lb2_strip_device_chunked (input resident, output streamed through two slots) hands the consumer the same bytes the
+    one-batch call produces, chunk after chunk, and reports the same per-file sizes / totals."""
+    import ctypes as C
+    from lambdipy_b200.corpus import Corpus
+    from lambdipy_b200.device import DeviceBatch
+    corpus = Corpus(120, seed=0xC0FFEE, max_size=8 << 20)
+    whole = DeviceBatch.from_corpus(gpu_ctx, corpus)
+    ring = DeviceBatch.from_corpus(gpu_ctx, corpus, chunk_bytes=24 << 20)      # ~8 chunks of whole files
+    try:
+        whole.strip_async()
+        st1 = whole.results()
+        want = [whole.read_output(i) for i in range(len(corpus))]
+        got, chunks = {}, []
+
+        def on_chunk(chunk, f0, n, d_slot, ooff, osz, status):
+            chunks.append((chunk, f0, n))
+            assert (status == 0).all()
+            for k in range(n):
+                buf = C.create_string_buffer(int(osz[k]))
+                gpu_ctx.d2h(buf, d_slot + int(ooff[k]), len(buf))
+                got[f0 + k] = buf.raw
+
+        st2 = ring.strip_chunked(on_chunk=on_chunk)
+        assert len(chunks) >= 4 and [c[0] for c in chunks] == list(range(len(chunks)))
+        assert sum(c[2] for c in chunks) == len(corpus) and chunks[0][1] == 0
+        assert [got[i] for i in range(len(corpus))] == want
+        for k in ("n_ok", "n_unsupported", "in_bytes", "out_bytes", "copy_bytes", "header_bytes", "n_tiles"):
+            assert st1[k] == st2[k], k
+        assert (ring.out_sizes[:len(corpus)] == whole.out_sizes[:len(corpus)]).all() and not ring.status[:len(corpus)].any()
+        for i in (0, 17, 63, 119):
+            rc, ob = oracle.strip(whole.read_input(i))
+            assert rc == 0 and ob == got[i]
+        st3 = ring.strip_chunked()        # no consumer: the benchmark's use
+        assert st3["out_bytes"] == st1["out_bytes"] and st3["n_ok"] == len(corpus)
+    finally:
+        whole.close(); ring.close()
+
+
 def test_output_capacity_error_is_reported(gpu_ctx, variants):
     from lambdipy_b200 import _native as N
     from lambdipy_b200.device import DeviceBatch
