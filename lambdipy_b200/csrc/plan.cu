@@ -88,6 +88,11 @@ struct PlanSmem {
   // build-attribute note workspace (phase E, warp 1) and the extent list (phases L/M) are never live together
   union { NoteWork n; ExtWork x; } u;
   // scalars shared by the CTA
+  int nflag[6];                 // note merging: corrupt, v1, v2 / ambiguous names, v3, not-an-order, walk verdict
+  int n_notes;
+  uint32_t n_newsize;
+  uint64_t defer_mask;          // note sections with more than 32 notes: merged by the whole CTA after the join
+  uint32_t defer_scr_used;
   int fail, fail_e, err_mal, err_uns, need_hoist, names_ambiguous;
   int nk, nent, n_ext, new_phnum;
   uint32_t keep32[2], alloc32[2], nobits32[2];
@@ -327,12 +332,20 @@ __device__ __forceinline__ int cmp_by_attr(const PlanSmem &sm, const uint8_t *nb
   if (a.type != 0x100 && b.type == 0x100) return 1;
   return 0;
 }
+// The note routines below run either on ONE warp (NT = 32: warp 1, next to the program-header and .shstrtab jobs --
+// the common case of a few notes) or on the WHOLE CTA (NT = 128: after the join, for sections with more than 32
+// notes, where the per-note and per-pair loops are worth spreading over four warps).  `t` is the thread's index in
+// the group; flags travel through shared memory; group_sync is __syncwarp or __syncthreads.
+template <int NT> __device__ __forceinline__ void group_sync() {
+  if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
 // objcopy sorts the notes with libc qsort(); its first comparator is not antisymmetric for nested
 // ranges, so the result depends on the exact comparison sequence.  This image's glibc 2.39 qsort
 // is the classic top-down merge sort (msort.c: n1 = n / 2, sort both halves, merge taking the left
 // element while cmp(left, right) <= 0).  The recursion tree is restated level by level: at depth d the
 // segment of node k is found by halving [0, n) along the bits of k, all merges of one depth are
-// independent and run on different lanes, deepest level first -- the same comparisons in the same
+// independent and run on different threads, deepest level first -- the same comparisons in the same
 // order inside every merge as the recursive routine, 2n instead of n log n merge steps deep.  Inside a
 // merge the heads of both runs live in registers and the element behind each head is already on its way
 // from shared memory while the heads are compared.
@@ -344,15 +357,15 @@ __device__ __forceinline__ void msort_node(int n, int depth, int k, int *lo, int
   }
   *lo = l; *hi = h;
 }
-template <bool FAST>
-__device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int lane) {
+template <int NT, bool FAST>
+__device__ void group_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int t) {
   const DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
   uint16_t *__restrict__ tmp = sm.u.n.tmp;
   int depth = 0;
   while ((1 << depth) < n) depth++;
   for (int d = depth - 1; d >= 0; d--) {
-    for (int k = lane; k < (1 << d); k += 32) {
+    for (int k = t; k < (1 << d); k += NT) {
       int lo, hi;
       msort_node(n, d, k, &lo, &hi);
       const int n1 = (hi - lo) / 2;
@@ -379,7 +392,7 @@ __device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int l
       while (r1 > 0) { tmp[w++] = perm[i++]; r1--; }
       for (int q = lo; q < w; q++) perm[q] = tmp[q];  // the tail of the right run is already in place
     }
-    __syncwarp();
+    group_sync<NT>();
   }
 }
 
@@ -392,16 +405,16 @@ __device__ void warp_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int l
 //                  equals (start, end, OPEN first) exactly when no note starts inside an earlier-starting note
 //                  of the same name without also ending behind it, and no note has start > end (see the case
 //                  analysis in DESIGN.md).  The pass checks that while it counts; if it fails, nothing has been
-//                  written and the caller runs the restated merge sort instead.
-template <bool FIRST>
-__device__ bool warp_ranksort_notes(PlanSmem &sm, int n, int lane) {
+//                  written to perm[] and the caller runs the restated merge sort instead.
+template <int NT, bool FIRST>
+__device__ bool group_ranksort_notes(PlanSmem &sm, int n, int t) {
   const DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
   uint16_t *__restrict__ tmp = sm.u.n.tmp;
-  int viol = 0;
-  for (int p0 = 0; p0 < n; p0 += 32) {
-    const int p = p0 + lane;
+  for (int p0 = 0; p0 < n; p0 += NT) {
+    const int p = p0 + t;
     if (p < n) {
+      int viol = 0;
       const uint16_t ip = perm[p];
       const DNote a = notes[ip];
       const bool a_open = a.type == 0x100;
@@ -424,12 +437,13 @@ __device__ bool warp_ranksort_notes(PlanSmem &sm, int n, int lane) {
         r += (c < 0) || (c == 0 && q < p);
       }
       tmp[r] = ip;
+      if (FIRST && viol) sm.nflag[4] = 1;
     }
-    if (FIRST && __ballot_sync(0xffffffffu, viol)) return false;   // not an order: stop after this round of 32
+    group_sync<NT>();
+    if (FIRST && sm.nflag[4]) return false;   // not an order: stop after this round
   }
-  __syncwarp();
-  for (int p = lane; p < n; p += 32) perm[p] = tmp[p];
-  __syncwarp();
+  for (int p = t; p < n; p += NT) perm[p] = tmp[p];
+  group_sync<NT>();
   return true;
 }
 
@@ -442,111 +456,116 @@ __device__ __forceinline__ uint64_t last_set_value(unsigned mask, uint64_t v, ui
 }
 
 #ifdef LB2_HOST_EMULATION   // the CPU emulator reports which sort path a file took, so the tests can insist both are covered
-static int lb2_path_counts[3];   // [0] rank sort, [1] merge sort with name ranks, [2] merge sort with full name compares
-#define LB2_COUNT(k) do { if (lane == 0) __atomic_fetch_add(&lb2_path_counts[k], 1, __ATOMIC_RELAXED); } while (0)
+static int lb2_path_counts[4];   // [0] rank sort, [1] merge sort with name ranks, [2] merge sort with full name compares, [3] sections merged by the whole CTA
+#define LB2_COUNT(k) do { if (t == 0) __atomic_fetch_add(&lb2_path_counts[k], 1, __ATOMIC_RELAXED); } while (0)
 #else
 #define LB2_COUNT(k) do { } while (0)
 #endif
 #ifdef LB2_PLAN_TIMING
-#define LB2_NT(k) do { __syncwarp(); if (lane == 0) nt_[k] = clock64(); } while (0)
+#define LB2_NT(k) do { group_sync<NT>(); if (t == 0) nt_[k] = clock64(); } while (0)
 #else
 #define LB2_NT(k) do { } while (0)
 #endif
-// Merges the `size` bytes of notes at nbuf (the shared-memory copy of the section) and writes the result to `out` (global scratch).
-// Returns the new size; *err: 1 = objcopy would report corrupt notes, 2 = more notes than the workspace
-// holds.  Warp-collective (one warp).
-__device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_t size, uint8_t *out, int *err, int lane) {
+
+// Step 1 of the merge, shared by both group sizes: one thread walks the variable-length records (three words each)
+// and records where every note starts.  Result in sm.n_notes / sm.nflag[5] (1 corrupt, 2 more notes than MAX_NOTES).
+__device__ __forceinline__ void walk_note_records(PlanSmem &sm, const uint8_t *nbuf, uint32_t size) {
+  DNote *__restrict__ notes = sm.u.n.notes;
+  uint16_t *__restrict__ perm = sm.u.n.perm;
+  int n = 0, e1 = 0;
+  uint32_t remain = size, p = 0;
+  while (remain >= 12) {
+    if (n >= MAX_NOTES) { e1 = 2; break; }
+    const uint32_t namesz = ldg32(nbuf + p), descsz = ldg32(nbuf + p + 4);
+    const uint64_t padded = ((uint64_t)namesz + 3) & ~3ull;   // 64-bit: namesz = 0xffffffff must not wrap to 0
+    if (((descsz + 3) & ~3u) != descsz) { e1 = 1; break; }
+    if (padded + descsz + 12 > remain) { e1 = 1; break; }
+    notes[n].off = (uint16_t)p;
+    perm[n] = (uint16_t)n;
+    remain -= 12 + padded + descsz;
+    p += 12 + padded + descsz;
+    n++;
+  }
+  if (!e1 && remain != 0) e1 = 1;
+  sm.n_notes = n;
+  sm.nflag[5] = e1;
+  sm.nflag[0] = sm.nflag[1] = sm.nflag[2] = sm.nflag[3] = sm.nflag[4] = 0;
+}
+
+// Merges the `size` bytes of notes at nbuf (the shared-memory copy of the section, already walked by
+// walk_note_records) and writes the result to `out` (global scratch).  Returns the new size; *err: 1 = objcopy
+// would report corrupt notes.  Collective over the NT threads of the group.
+template <int NT>
+__device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_t size, uint8_t *out, int *err, int t) {
   DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
   uint16_t *__restrict__ tmp = sm.u.n.tmp;
   uint64_t *__restrict__ nkey = sm.u.n.key;
+  const int lane = t & 31;
 #ifdef LB2_PLAN_TIMING
   long long nt_[10];
 #endif
   LB2_NT(0);
-  // 1. lane 0 walks the variable-length records (three words each) and records where every note starts
-  int n = 0, e1 = 0;
-  if (lane == 0) {
-    uint32_t remain = size, p = 0;
-    while (remain >= 12) {
-      if (n >= MAX_NOTES) { e1 = 2; break; }
-      const uint32_t namesz = ldg32(nbuf + p), descsz = ldg32(nbuf + p + 4);
-      const uint64_t padded = ((uint64_t)namesz + 3) & ~3ull;   // 64-bit: namesz = 0xffffffff must not wrap to 0
-      if (((descsz + 3) & ~3u) != descsz) { e1 = 1; break; }
-      if (padded + descsz + 12 > remain) { e1 = 1; break; }
-      notes[n].off = (uint16_t)p;
-      perm[n] = (uint16_t)n;
-      remain -= 12 + padded + descsz;
-      p += 12 + padded + descsz;
-      n++;
+  const int n = sm.n_notes;
+  // 2. every thread decodes its notes: checks, raw range, version class, comparison key and name hash
+  for (int i = t; i < n; i += NT) {
+    DNote &d = notes[i];
+    const uint8_t *h = nbuf + d.off;
+    const uint32_t namesz = ldg32(h), descsz = ldg32(h + 4), type = ldg32(h + 8);
+    const uint32_t padded = (namesz + 3) & ~3u;
+    if (type != 0x100 && type != 0x101) { sm.nflag[0] = 1; continue; }
+    if (namesz < 3) { sm.nflag[0] = 1; continue; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
+    const uint8_t *nm = h + 12;
+    const uint8_t *dw = h + 12 + padded;
+    d.namesz = (uint16_t)namesz;
+    d.type = (uint16_t)type;
+    d.ver = 0; d.pad = 0; d.nrank = 0;
+    const uint8_t c0 = nm[0], c1 = nm[1], c2 = nm[2];
+    if (c0 == '$' && c1 == 1 && c2 == '1') sm.nflag[1] = 1;
+    else if (namesz > 4 && c0 == 'G' && c1 == 'A' && c2 == '$' && nm[3] == 1) {
+      d.ver = 1;
+      const uint8_t c4 = nm[4];
+      if (c4 == '2') sm.nflag[2] = 1;
+      else if (c4 == '3') sm.nflag[3] = 1;
+      else { sm.nflag[0] = 1; continue; }
     }
-    if (!e1 && remain != 0) e1 = 1;
+    uint64_t start, end;
+    if (descsz == 0) start = end = 0;
+    else if (descsz == 4) { start = ldg32(dw); end = ~0ull; }
+    else if (descsz == 8) { start = ldg32(dw); end = ldg32(dw + 4); }
+    else if (descsz == 16) { start = (uint64_t)ldg32(dw) | ((uint64_t)ldg32(dw + 4) << 32); end = (uint64_t)ldg32(dw + 8) | ((uint64_t)ldg32(dw + 12) << 32); }
+    else { sm.nflag[0] = 1; continue; }
+    if (start > end) start = end;
+    d.start = start;   // raw; ranges inherited from earlier notes are filled in by step 3
+    d.end = end;
+    if (nm[namesz - 1] != 0) { sm.nflag[0] = 1; continue; }
+    uint64_t key = 0;
+    uint32_t hsh = 2166136261u;
+    for (int q = 0; q < (int)namesz; q++) {
+      const uint8_t ch = nm[q];
+      hsh = (hsh ^ ch) * 16777619u;
+      if (q >= 3 && q < 11) key = (key << 8) | ch;
+    }
+    if (namesz <= 3) key = 0; else if (namesz < 11) key <<= 8 * (11 - namesz);
+    nkey[i] = key;
+    d.tag = (hsh << 10) ^ namesz;
   }
-  n = __shfl_sync(0xffffffffu, n, 0);
-  e1 = __shfl_sync(0xffffffffu, e1, 0);
-  __syncwarp();
-  if (e1) { *err = e1; return size; }
-  // 2. every lane decodes its notes: checks, raw range, version class, comparison key and name hash
+  group_sync<NT>();
   {
-    int bad = 0, v1 = 0, v2 = 0, v3 = 0;
-    for (int i = lane; i < n; i += 32) {
-      DNote &d = notes[i];
-      const uint8_t *h = nbuf + d.off;
-      const uint32_t namesz = ldg32(h), descsz = ldg32(h + 4), type = ldg32(h + 8);
-      const uint32_t padded = (namesz + 3) & ~3u;
-      if (type != 0x100 && type != 0x101) { bad = 1; continue; }
-      if (namesz < 3) { bad = 1; continue; }  // objcopy accepts 2 and then compares namesz - 3 bytes: treat as corrupt
-      const uint8_t *nm = h + 12;
-      const uint8_t *dw = h + 12 + padded;
-      d.namesz = (uint16_t)namesz;
-      d.type = (uint16_t)type;
-      d.ver = 0; d.pad = 0; d.nrank = 0;
-      const uint8_t c0 = nm[0], c1 = nm[1], c2 = nm[2];
-      if (c0 == '$' && c1 == 1 && c2 == '1') v1 = 1;
-      else if (namesz > 4 && c0 == 'G' && c1 == 'A' && c2 == '$' && nm[3] == 1) {
-        d.ver = 1;
-        const uint8_t c4 = nm[4];
-        if (c4 == '2') v2 = 1;
-        else if (c4 == '3') v3 = 1;
-        else { bad = 1; continue; }
-      }
-      uint64_t start, end;
-      if (descsz == 0) start = end = 0;
-      else if (descsz == 4) { start = ldg32(dw); end = ~0ull; }
-      else if (descsz == 8) { start = ldg32(dw); end = ldg32(dw + 4); }
-      else if (descsz == 16) { start = (uint64_t)ldg32(dw) | ((uint64_t)ldg32(dw + 4) << 32); end = (uint64_t)ldg32(dw + 8) | ((uint64_t)ldg32(dw + 12) << 32); }
-      else { bad = 1; continue; }
-      if (start > end) start = end;
-      d.start = start;   // raw; ranges inherited from earlier notes are filled in by step 3
-      d.end = end;
-      if (nm[namesz - 1] != 0) { bad = 1; continue; }
-      uint64_t key = 0;
-      uint32_t hsh = 2166136261u;
-      for (int q = 0; q < (int)namesz; q++) {
-        const uint8_t ch = nm[q];
-        hsh = (hsh ^ ch) * 16777619u;
-        if (q >= 3 && q < 11) key = (key << 8) | ch;
-      }
-      if (namesz <= 3) key = 0; else if (namesz < 11) key <<= 8 * (11 - namesz);
-      nkey[i] = key;
-      d.tag = (hsh << 10) ^ namesz;
-    }
-    const unsigned mb = __ballot_sync(0xffffffffu, bad), m1 = __ballot_sync(0xffffffffu, v1), m2 = __ballot_sync(0xffffffffu, v2),
-                   m3 = __ballot_sync(0xffffffffu, v3);
-    if (mb) { *err = 1; return size; }
-    bool a1 = m1 != 0, a2 = m2 != 0, a3 = m3 != 0;
+    if (sm.nflag[0]) { *err = 1; return size; }
+    bool a1 = sm.nflag[1] != 0, a2 = sm.nflag[2] != 0, a3 = sm.nflag[3] != 0;
     if (!a1 && !a2 && !a3) a3 = true;  // "version note missing - assuming version 3"
     if ((a1 && a2) || (a1 && a3) || (a2 && a3)) { *err = 1; return size; }
     if (!a3 || size < 12) {            // only v3 notes are merged
-      for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
+      for (uint32_t i = t; i < size; i += NT) out[i] = nbuf[i];
       return size;
     }
   }
-  __syncwarp();
   LB2_NT(1);
   // 3. a note without a range inherits the previous OPEN / FUNC note's ("if (start) pos = start; start = pos"):
   //    the nearest earlier note of the same kind with a non-zero raw value, found with ballots, 32 notes a round
-  {
+  //    (the first warp of the group)
+  if (t < 32) {
     uint64_t pos = 0, poe = 0, pfs = 0, pfe = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
       const int i = i0 + lane;
@@ -563,9 +582,9 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       pfs = __shfl_sync(0xffffffffu, fs, 31); pfe = __shfl_sync(0xffffffffu, fe, 31);
     }
   }
-  __syncwarp();
   // 4. equality classes of the names (first note with identical name), one packed tag compare per candidate
-  for (int i = lane; i < n; i += 32) {
+  //    (independent of step 3: different fields)
+  for (int i = t; i < n; i += NT) {
     DNote &d = notes[i];
     const uint8_t *nm = nbuf + d.off + 12;
     const uint32_t tag = d.tag;
@@ -583,35 +602,35 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
     }
     d.cls = (uint16_t)cls;
   }
-  __syncwarp();
+  group_sync<NT>();
   // 4b. rank of every distinct name among the distinct names; if two distinct names compare equal (one is
   //     a prefix of the other beyond byte 3) ranks cannot stand in for the comparator: slow path
-  int amb = 0;
-  for (int i = lane; i < n; i += 32) {
+  for (int i = t; i < n; i += NT) {
     const DNote d = notes[i];
     if (d.cls != i) continue;
     const uint64_t ki = nkey[i];
-    int less = 0;
+    int less = 0, amb1 = 0;
     for (int j = 0; j < n; j++) {
       if (j == i || notes[j].cls != j) continue;
       const int c = cmp_note_names(sm, nbuf, notes[j], nkey[j], d, ki);
       less += c < 0;
-      amb |= c == 0;
+      amb1 |= c == 0;
     }
     notes[i].nrank = (uint16_t)less;
+    if (amb1) sm.nflag[1] = 1;   // (nflag[1..3] are free again: version flags were consumed above, behind a group sync)
   }
-  amb = __ballot_sync(0xffffffffu, amb) != 0;
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) if (notes[i].cls != i) notes[i].nrank = notes[notes[i].cls].nrank;
-  __syncwarp();
+  group_sync<NT>();
+  const bool amb = sm.nflag[1] != 0;
+  for (int i = t; i < n; i += NT) if (notes[i].cls != i) notes[i].nrank = notes[notes[i].cls].nrank;
+  group_sync<NT>();
   LB2_NT(2);
-  if (amb) { LB2_COUNT(2); warp_msort_notes<false>(sm, nbuf, n, lane); }   // restated glibc merge sort, level by level across lanes
-  else if (warp_ranksort_notes<true>(sm, n, lane)) LB2_COUNT(0);
-  else { LB2_COUNT(1); warp_msort_notes<true>(sm, nbuf, n, lane); }
+  if (amb) { LB2_COUNT(2); group_msort_notes<NT, false>(sm, nbuf, n, t); }   // restated glibc merge sort, level by level
+  else if (group_ranksort_notes<NT, true>(sm, n, t)) LB2_COUNT(0);
+  else { LB2_COUNT(1); group_msort_notes<NT, true>(sm, nbuf, n, t); }
   LB2_NT(3);
   // 5. objcopy's merge pass: every note looks back over the SURVIVING notes of the same attribute (at most 17).
   //    The survivors so far are kept as a stack in tmp[], so deleted notes cost nothing to skip.
-  if (lane == 0) {
+  if (t == 0) {
     int nl = 0;
     for (int i = 0; i < n; i++) {
       const uint16_t pi = perm[i];
@@ -642,14 +661,13 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       else tmp[nl++] = pi;
     }
   }
-  __syncwarp();
+  group_sync<NT>();
   LB2_NT(4);
-  warp_ranksort_notes<false>(sm, n, lane);
+  group_ranksort_notes<NT, false>(sm, n, t);
   LB2_NT(5);
   // 6. output offsets and range elision: a surviving note drops its description when its range equals the
-  //    previous survivor's.  Ballot + shuffle scan, 32 sorted positions a round.
-  uint32_t newsize = 0;
-  {
+  //    previous survivor's.  Ballot + shuffle scan, 32 sorted positions a round (the first warp of the group).
+  if (t < 32) {
     uint64_t ps = 0, pe = 0;
     uint32_t run = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -668,7 +686,7 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
       const uint32_t v = surv ? 12u + ((pn.namesz + 3u) & ~3u) + (elide ? 0u : 16u) : 0u;
       uint32_t inc = v;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
       if (i < n) tmp[i] = surv ? (uint16_t)(((run + inc - v) >> 2) | (elide ? 0x8000u : 0u)) : (uint16_t)0xffff;  // offsets are multiples of 4, < 64 KB
       run += __shfl_sync(0xffffffffu, inc, 31);
       if (ms) {
@@ -676,20 +694,21 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
         ps = __shfl_sync(0xffffffffu, pn.start, last); pe = __shfl_sync(0xffffffffu, pn.end, last);
       }
     }
-    newsize = run;
+    if (t == 0) sm.n_newsize = run;
   }
-  __syncwarp();
+  group_sync<NT>();
+  const uint32_t newsize = sm.n_newsize;
   if (newsize >= size) {  // objcopy keeps the original contents unless the merged notes are smaller
-    for (uint32_t i = lane; i < size; i += 32) out[i] = nbuf[i];
-    __syncwarp();
+    for (uint32_t i = t; i < size; i += NT) out[i] = nbuf[i];
+    group_sync<NT>();
     return size;
   }
-  for (int i = lane; i < n; i += 32) {
-    const uint16_t t = tmp[i];
-    if (t == 0xffff) continue;
+  for (int i = t; i < n; i += NT) {
+    const uint16_t tt = tmp[i];
+    if (tt == 0xffff) continue;
     const DNote pn = notes[perm[i]];
-    const bool elide = (t & 0x8000u) != 0;
-    uint8_t *o = out + ((uint32_t)(t & 0x7fffu) << 2);
+    const bool elide = (tt & 0x8000u) != 0;
+    uint8_t *o = out + ((uint32_t)(tt & 0x7fffu) << 2);
     const uint32_t padded = (pn.namesz + 3u) & ~3u;
     wr32(o, pn.namesz);
     wr32(o + 4, elide ? 0u : 16u);
@@ -698,10 +717,10 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
     for (uint32_t q = 0; q < padded; q++) o[12 + q] = q < pn.namesz ? nm[q] : 0;
     if (!elide) { wr64(o + 12 + padded, pn.start); wr64(o + 20 + padded, pn.end); }
   }
-  __syncwarp();
+  group_sync<NT>();
   LB2_NT(6);
 #ifdef LB2_PLAN_TIMING
-  if (lane == 0 && blockIdx.x == 0) printf("  notes n=%d amb=%d: parse=%lld aids=%lld sort1=%lld merge=%lld sort2=%lld out=%lld\n", n, amb, nt_[1]-nt_[0], nt_[2]-nt_[1], nt_[3]-nt_[2], nt_[4]-nt_[3], nt_[5]-nt_[4], nt_[6]-nt_[5]);
+  if (t == 0 && blockIdx.x == 0) printf("  notes n=%d amb=%d threads=%d: parse=%lld aids=%lld sort1=%lld merge=%lld sort2=%lld out=%lld\n", n, (int)amb, NT, nt_[1]-nt_[0], nt_[2]-nt_[1], nt_[3]-nt_[2], nt_[4]-nt_[3], nt_[5]-nt_[4], nt_[6]-nt_[5]);
 #endif
   return newsize;
 }
@@ -753,7 +772,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
   // ---- A. Ehdr (every exit below is taken by the whole CTA: verdicts come from shared memory)
   if (n < 64) LB2_REJECT(ST_NOT_ELF);
   if (tid < 4) reinterpret_cast<uint4 *>(&sm.eh)[tid] = __ldg(reinterpret_cast<const uint4 *>(in) + tid);
-  if (tid == 0) { sm.fail = 0; sm.fail_e = 0; sm.err_mal = 0; sm.err_uns = 0; sm.need_hoist = 0; sm.names_ambiguous = 0; sm.note_hdr_bytes = 0; }
+  if (tid == 0) { sm.fail = 0; sm.fail_e = 0; sm.defer_mask = 0; sm.defer_scr_used = 0; sm.err_mal = 0; sm.err_uns = 0; sm.need_hoist = 0; sm.names_ambiguous = 0; sm.note_hdr_bytes = 0; }
   __syncthreads();
   const Ehdr &eh = sm.eh;
   int st = ST_OK;
@@ -1163,7 +1182,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     if (lane == 0) sm.t_warp[0] = clock64();
 #endif
   } else if (warp == 1) {
-    // ---- E. R9 build-attribute note merging (the new sizes feed the non-alloc layout after the join)
+    // ---- E. R9 build-attribute note merging (the new sizes feed the non-alloc layout after the join).
+    //         Sections with up to 32 notes are merged right here by this warp; the first bigger one sends itself
+    //         and everything behind it to the whole CTA (after the join).
     if (!(a.flags & 1u)) {
       uint32_t scr_used = 0;
       int nfail = 0;
@@ -1177,8 +1198,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
         uint8_t *dst = scr + SCR_NOTES + scr_used;
         warp_g2s(sm.u.n.buf, in + h.sh_offset, (uint32_t)h.sh_size, lane);
         __syncwarp();
-        const uint32_t ns = merge_build_notes(sm, sm.u.n.buf, (uint32_t)h.sh_size, dst, &err, lane);
-        if (err) { nfail = err == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES; break; }
+        if (lane == 0) walk_note_records(sm, sm.u.n.buf, (uint32_t)h.sh_size);
+        __syncwarp();
+        if (sm.nflag[5]) { nfail = sm.nflag[5] == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES; break; }
+        if (sm.n_notes > 32) {
+          if (lane == 0) { sm.defer_mask = mq; sm.defer_scr_used = scr_used; }
+          break;
+        }
+        const uint32_t ns = merge_build_notes<32>(sm, sm.u.n.buf, (uint32_t)h.sh_size, dst, &err, lane);
+        if (err) { nfail = ST_BAD_NOTES; break; }
         if (lane == 0) {
           sm.new_size[i] = ns;
           sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
@@ -1326,6 +1354,40 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
 #endif
   }
   __syncthreads();
+  if (sm.defer_mask && !sm.fail_e) {
+    // ---- E'. note sections with more than 32 notes: the same merge, every per-note and per-pair loop spread over
+    //          the four warps (the other jobs are done, the CTA would idle behind warp 1 otherwise)
+    uint32_t scr_used = sm.defer_scr_used;
+    int nfail = 0;
+    for (uint64_t mq = sm.defer_mask; mq && !nfail; mq &= mq - 1) {
+      const int i = __ffsll((long long)mq) - 1;
+      const Shdr &h = sm.sh[i];
+      if (h.sh_type != SHT_NOTE) continue;
+      if (!d_prefix(sm.names + h.sh_name, ".gnu.build.attributes")) continue;
+      if (h.sh_size > (uint64_t)MAX_NOTE_BYTES || scr_used + h.sh_size > MAX_NOTE_BYTES) { nfail = ST_PLANNER_LIMIT; break; }
+      int err = 0;
+      uint8_t *dst = scr + SCR_NOTES + scr_used;
+      __syncthreads();   // the previous section's workspace is no longer read
+      block_g2s(sm.u.n.buf, in + h.sh_offset, (uint32_t)h.sh_size, tid);
+      __syncthreads();
+      if (tid == 0) walk_note_records(sm, sm.u.n.buf, (uint32_t)h.sh_size);
+      __syncthreads();
+      if (sm.nflag[5]) { nfail = sm.nflag[5] == 2 ? ST_PLANNER_LIMIT : ST_BAD_NOTES; break; }
+#ifdef LB2_HOST_EMULATION
+      { const int t = tid; LB2_COUNT(3); }
+#endif
+      const uint32_t ns = merge_build_notes<PLAN_THREADS>(sm, sm.u.n.buf, (uint32_t)h.sh_size, dst, &err, tid);
+      if (err) { nfail = ST_BAD_NOTES; break; }
+      if (tid == 0) {
+        sm.new_size[i] = ns;
+        sm.src_addr[i] = reinterpret_cast<uint64_t>(dst);
+        sm.note_hdr_bytes += h.sh_size;
+      }
+      scr_used += (ns + 15u) & ~15u;
+    }
+    __syncthreads();
+    if (nfail) LB2_REJECT(nfail);
+  }
   if (sm.fail_e || sm.fail) LB2_REJECT(sm.fail_e ? sm.fail_e : sm.fail);
   LB2_T(5);
 

@@ -128,4 +128,4 @@ extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8
   return rc;
 }
 extern "C" void lb2emu_free(uint8_t *p) { free(p); }
-extern "C" void lb2emu_path_counts(int *out) { for (int k = 0; k < 3; k++) out[k] = lb2::lb2_path_counts[k]; }
+extern "C" void lb2emu_path_counts(int *out) { for (int k = 0; k < 4; k++) out[k] = lb2::lb2_path_counts[k]; }

@@ -27,8 +27,8 @@ class Emu:
         self.lib.lb2emu_free.argtypes = [ctypes.c_void_p]
 
     def path_counts(self):
-        """[rank-sorted, merge-sorted by name rank, merge-sorted with full name compares] note sections so far"""
-        out = (ctypes.c_int * 3)()
+        """[rank-sorted, merge-sorted by name rank, merge-sorted with full name compares, merged by the whole CTA] note sections so far"""
+        out = (ctypes.c_int * 4)()
         self.lib.lb2emu_path_counts(out)
         return list(out)
 

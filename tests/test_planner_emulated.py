@@ -73,6 +73,7 @@ def test_random_notes_and_structure_fuzz(emu, oracle, variants, fixture_dir, tmp
         assert _agree(emu, oracle, _read(p)) == 0
     c1 = emu.path_counts()
     assert c1[0] - c0[0] > 10 and c1[1] - c0[1] > 2, (c0, c1)   # proper orders took the rank sort, the nested ones fell back
+    assert c0[3] > 10 and c1[3] - c0[3] > 10, (c0, c1)           # sections with more than 32 notes went to the whole CTA
     seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
     accepted = 0
     for k in range(300):
