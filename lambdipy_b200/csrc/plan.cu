@@ -407,44 +407,111 @@ __device__ void group_msort_notes(PlanSmem &sm, const uint8_t *nbuf, int n, int 
 //                  analysis in DESIGN.md).  The pass checks that while it counts; if it fails, nothing has been
 //                  written to perm[] and the caller runs the restated merge sort instead.
 template <int NT, bool FIRST>
-__device__ bool group_ranksort_notes(PlanSmem &sm, int n, int t) {
+__device__ void group_ranksort_notes(PlanSmem &sm, int n, int t) {
+  DNote *__restrict__ notes = sm.u.n.notes;
+  uint16_t *__restrict__ perm = sm.u.n.perm;
+  uint16_t *__restrict__ tmp = sm.u.n.tmp;
+  for (int p = t; p < n; p += NT) {
+    int viol = 0;
+    const uint16_t ip = perm[p];
+    const DNote a = notes[ip];
+    const bool a_open = a.type == 0x100;
+    if (FIRST && a.start > a.end) viol = 1;
+    int r = 0;
+#pragma unroll 2
+    for (int q = 0; q < n; q++) {
+      const DNote b = notes[perm[q]];
+      const bool b_open = b.type == 0x100;
+      int c;  // sign of compare(b, a)
+      if (FIRST) {
+        if (b.nrank != a.nrank) c = b.nrank < a.nrank ? -1 : 1;
+        else {
+          if (b.start < a.start && a.start <= b.end && a.end <= b.end) viol = 1;
+          c = b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end < a.end ? -1 : 1) : (b_open == a_open ? 0 : (b_open ? -1 : 1));
+        }
+      } else {
+        c = b_open != a_open ? (b_open ? -1 : 1) : b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end > a.end ? -1 : 1) : 0;
+      }
+      r += (c < 0) || (c == 0 && q < p);
+    }
+    tmp[r] = ip;
+    if (FIRST && viol) notes[a.cls].pad = 1;   // this attribute's notes are not ordered by the comparator: see below
+  }
+  group_sync<NT>();
+  for (int p = t; p < n; p += NT) perm[p] = tmp[p];
+  group_sync<NT>();
+}
+
+// The first sort when the names ARE totally ordered but some attribute has nested ranges.  Comparisons between
+// notes of different attributes are consistent, so every merge of the library sort interleaves two runs attribute
+// by attribute: the final order is the attributes in rank order, and inside one attribute exactly what the same
+// merge sort does to that attribute's notes alone -- split points taken from the GLOBAL recursion tree ([lo,hi) ->
+// [lo,mid), [mid,hi) over the original indices), merges taking the left element while cmp <= 0.  The rank sort
+// has already put every attribute's notes into one contiguous stretch of perm[] (right for the attributes whose
+// comparator is an order); for the others one thread per attribute replays the restricted merge sort: O(m log n)
+// sequential steps for m notes instead of 2n for the whole section, all such attributes at once.
+template <int NT>
+__device__ void group_fix_nested_classes(PlanSmem &sm, const uint8_t *nbuf, int n, int t) {
   const DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
   uint16_t *__restrict__ tmp = sm.u.n.tmp;
-  for (int p0 = 0; p0 < n; p0 += NT) {
-    const int p = p0 + t;
-    if (p < n) {
-      int viol = 0;
-      const uint16_t ip = perm[p];
-      const DNote a = notes[ip];
-      const bool a_open = a.type == 0x100;
-      if (FIRST && a.start > a.end) viol = 1;
-      int r = 0;
-#pragma unroll 2
-      for (int q = 0; q < n; q++) {
-        const DNote b = notes[perm[q]];
-        const bool b_open = b.type == 0x100;
-        int c;  // sign of compare(b, a)
-        if (FIRST) {
-          if (b.nrank != a.nrank) c = b.nrank < a.nrank ? -1 : 1;
-          else {
-            if (b.start < a.start && a.start <= b.end && a.end <= b.end) viol = 1;
-            c = b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end < a.end ? -1 : 1) : (b_open == a_open ? 0 : (b_open ? -1 : 1));
-          }
-        } else {
-          c = b_open != a_open ? (b_open ? -1 : 1) : b.start != a.start ? (b.start < a.start ? -1 : 1) : b.end != a.end ? (b.end > a.end ? -1 : 1) : 0;
-        }
-        r += (c < 0) || (c == 0 && q < p);
-      }
-      tmp[r] = ip;
-      if (FIRST && viol) sm.nflag[4] = 1;
+  for (int rep = t; rep < n; rep += NT) {
+    if (notes[rep].cls != rep || !notes[rep].pad) continue;
+    // the attribute's stretch of perm[]
+    int p0 = 0;
+    while (p0 < n && notes[perm[p0]].cls != rep) p0++;
+    int p1 = p0;
+    while (p1 < n && notes[perm[p1]].cls == rep) p1++;
+    // back to original order (the values ARE the original indices): insertion sort
+    for (int i = p0 + 1; i < p1; i++) {
+      const uint16_t v = perm[i];
+      int j = i - 1;
+      while (j >= p0 && perm[j] > v) { perm[j + 1] = perm[j]; j--; }
+      perm[j + 1] = v;
     }
-    group_sync<NT>();
-    if (FIRST && sm.nflag[4]) return false;   // not an order: stop after this round
+    // msort_with_tmp over the global index tree, restricted to this stretch; explicit stack (depth <= log2(MAX_NOTES) + 2)
+    int f_lo[12], f_hi[12], f_a[12], f_b[12], f_s[12], f_stage[12];
+    int sp = 0;
+    f_lo[0] = 0; f_hi[0] = n; f_a[0] = p0; f_b[0] = p1; f_s[0] = 0; f_stage[0] = 0;
+    while (sp >= 0) {
+      const int lo = f_lo[sp], hi = f_hi[sp], a = f_a[sp], b = f_b[sp];
+      if (b - a <= 1 || hi - lo <= 1) { sp--; continue; }
+      const int mid = lo + (hi - lo) / 2;
+      if (f_stage[sp] == 0) {
+        int sidx = a;
+        while (sidx < b && (int)perm[sidx] < mid) sidx++;   // still in original order: no descendant has run yet
+        f_s[sp] = sidx; f_stage[sp] = 1;
+        sp++; f_lo[sp] = lo; f_hi[sp] = mid; f_a[sp] = a; f_b[sp] = sidx; f_stage[sp] = 0;
+      } else if (f_stage[sp] == 1) {
+        f_stage[sp] = 2;
+        const int sidx = f_s[sp];
+        sp++; f_lo[sp] = mid; f_hi[sp] = hi; f_a[sp] = sidx; f_b[sp] = b; f_stage[sp] = 0;
+      } else {
+        const int sidx = f_s[sp];
+        int i = a, j = sidx, w = a, r1 = sidx - a, r2 = b - sidx;
+        if (r1 > 0 && r2 > 0) {
+          uint16_t pa = perm[i], pb = perm[j];
+          DNote na = notes[pa], nb = notes[pb];
+          while (true) {
+            const int c = cmp_by_attr<true>(sm, nbuf, na, pa, nb, pb);
+            if (c <= 0) {
+              tmp[w++] = pa; i++;
+              if (--r1 == 0) break;
+              pa = perm[i]; na = notes[pa];
+            } else {
+              tmp[w++] = pb; j++;
+              if (--r2 == 0) break;
+              pb = perm[j]; nb = notes[pb];
+            }
+          }
+          while (r1 > 0) { tmp[w++] = perm[i++]; r1--; }
+          for (int q = a; q < w; q++) perm[q] = tmp[q];  // the tail of the right run is already in place
+        }
+        sp--;
+      }
+    }
   }
-  for (int p = t; p < n; p += NT) perm[p] = tmp[p];
   group_sync<NT>();
-  return true;
 }
 
 // 64-bit value of the nearest lane at or below `lane` whose bit is set in `mask`, else `carry`
@@ -625,8 +692,13 @@ __device__ uint32_t merge_build_notes(PlanSmem &sm, const uint8_t *nbuf, uint32_
   group_sync<NT>();
   LB2_NT(2);
   if (amb) { LB2_COUNT(2); group_msort_notes<NT, false>(sm, nbuf, n, t); }   // restated glibc merge sort, level by level
-  else if (group_ranksort_notes<NT, true>(sm, n, t)) LB2_COUNT(0);
-  else { LB2_COUNT(1); group_msort_notes<NT, true>(sm, nbuf, n, t); }
+  else {
+    group_ranksort_notes<NT, true>(sm, n, t);
+#ifdef LB2_HOST_EMULATION
+    { int any = 0; for (int i = 0; i < n; i++) any |= notes[i].pad; if (any) LB2_COUNT(1); else LB2_COUNT(0); }
+#endif
+    group_fix_nested_classes<NT>(sm, nbuf, n, t);
+  }
   LB2_NT(3);
   // 5. objcopy's merge pass: every note looks back over the SURVIVING notes of the same attribute (at most 17).
   //    The survivors so far are kept as a stack in tmp[], so deleted notes cost nothing to skip.
@@ -1613,21 +1685,32 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     if (tid == 0) { a.ctr->overflow = 1; a.status[f] = ST_PLANNER_LIMIT; a.out_size[f] = 0; }
     return;
   }
-  auto emit_tiles = [&](int e, uint32_t k, const uint32_t step) {
+  auto emit_tiles = [&](int e, const uint32_t k0, const uint32_t step) {
     const uint64_t d = sm.u.x.dst[e], l = sm.u.x.len[e], s = sm.u.x.src[e];
     if (l == 0) return;
     const uint64_t t0 = d / TILE_BYTES;
     const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - t0 + 1);
     Tile *out = a.tiles + tile_base + sm.u.x.tiles[e];
-#pragma unroll 4
-    for (; k < cnt; k += step) {
-      uint64_t b = (t0 + k) * TILE_BYTES, en = b + TILE_BYTES;
-      if (b < d) b = d;
-      if (en > d + l) en = d + l;
+    const uint64_t sbase = s - d;   // source address of output byte b is sbase + b (copies; zero fills keep src = 0)
+    if (k0 == 0) {                  // the two edge tiles are the only clipped ones
       Tile t;
-      t.src = s ? s + (b - d) : 0;
+      t.file = f;
+      const uint64_t e0 = (t0 + 1) * TILE_BYTES < d + l ? (t0 + 1) * TILE_BYTES : d + l;
+      t.src = s; t.dst_rel = d; t.len = (uint32_t)(e0 - d);
+      out[0] = t;
+      if (cnt > 1) {
+        const uint64_t b = (t0 + cnt - 1) * TILE_BYTES;
+        t.src = s ? sbase + b : 0; t.dst_rel = b; t.len = (uint32_t)(d + l - b);
+        out[cnt - 1] = t;
+      }
+    }
+#pragma unroll 4
+    for (uint32_t k = 1 + k0; k + 1 < cnt; k += step) {   // interior tiles: whole, aligned
+      const uint64_t b = (t0 + k) * TILE_BYTES;
+      Tile t;
+      t.src = s ? sbase + b : 0;
       t.dst_rel = b;
-      t.len = (uint32_t)(en - b);
+      t.len = TILE_BYTES;
       t.file = f;
       out[k] = t;
     }

@@ -34,6 +34,10 @@ def test_random_note_sections_gpu(gpu_ctx, oracle, variants, fixture_dir):
         p = os.path.join(fixture_dir, "gpu_stair_notes_%d.so" % case)
         assert F.with_build_notes(variants["c_plain"], p, _staircase_notes(rng, rng.choice([4, 12, 40, 90, 130])))
         blobs.append(open(p, "rb").read())
+    for case in range(40):   # attribute names that are prefixes of each other: the slow, fully sequential sort
+        p = os.path.join(fixture_dir, "gpu_pfx_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([5, 12, 30, 70, 120]), prefix_names=True))
+        blobs.append(open(p, "rb").read())
     outs, status, _ = S.strip_buffers(gpu_ctx, blobs)
     for i, (b, o, st) in enumerate(zip(blobs, outs, status)):
         rc, want = oracle.strip(b)

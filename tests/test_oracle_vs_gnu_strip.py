@@ -61,10 +61,12 @@ def test_build_attribute_notes(oracle, note_files, tmp_path, no_merge):
         assert gnu is not None and rc == 0 and out == gnu, name
 
 
-def _random_notes(rng, n):
+def _random_notes(rng, n, prefix_names=False):
     O, Fn = 0x100, 0x101
     names = [F.GA_VERSION, b"GA*\x02\x03\x00", b"GA*\x07\x02\x00", b"GA*FORTIFY\x00\x02\x00", b"GA$\x05gcc 13\x00",
              b"GA+stack_clash\x00", b"GA!\x08\x00", b"GA*GOW\x00\x2a\x05\x02\x00", b"GA*GOW\x00\x2a\x05\x00"]
+    if prefix_names:  # names that compare EQUAL over the shorter length (memcmp from byte 3): the name order stops being one
+        names += [b"GA*GOW\x00\x2a\x05\x00\x00", b"GA+stack_clash\x00\x01\x00", b"GA!\x08\x00\x00", b"GA*\x00"]
     notes = [(F.GA_VERSION, O, (0x1000, 0x1000 + rng.randrange(1, 0x400)))]
     for _ in range(n):
         nm = rng.choice(names)
@@ -133,6 +135,19 @@ def test_random_note_sections(oracle, variants, fixture_dir, tmp_path):
         data, gnu, rc, out, err = _diff(oracle, p, str(tmp_path))
         assert gnu is not None, err
         assert rc == 0 and out == gnu, "random note case %d" % case
+
+
+def test_note_names_that_are_prefixes_of_each_other(oracle, variants, fixture_dir, tmp_path):
+    """objcopy compares attribute names over the SHORTER length: a name that continues another compares equal to it but
+    not to a third one -- the sort then depends on the comparison sequence even across names"""
+    rng = random.Random(9091)
+    for case in range(30):
+        notes = _random_notes(rng, rng.choice([5, 12, 30, 70, 120]), prefix_names=True)
+        p = os.path.join(fixture_dir, "pfx_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, notes)
+        data, gnu, rc, out, err = _diff(oracle, p, str(tmp_path))
+        assert gnu is not None, err
+        assert rc == 0 and out == gnu, "prefix-name note case %d" % case
 
 
 def test_doctored_edges(oracle, doctored, tmp_path):

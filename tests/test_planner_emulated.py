@@ -71,7 +71,12 @@ def test_random_notes_and_structure_fuzz(emu, oracle, variants, fixture_dir, tmp
         p = os.path.join(fixture_dir, "emu_stair_notes_%d.so" % case)
         assert F.with_build_notes(variants["c_plain"], p, _staircase_notes(rng, rng.choice([4, 12, 40, 90, 130])))
         assert _agree(emu, oracle, _read(p)) == 0
+    for case in range(30):
+        p = os.path.join(fixture_dir, "emu_pfx_notes_%d.so" % case)
+        assert F.with_build_notes(variants["c_plain"], p, _random_notes(rng, rng.choice([5, 12, 30, 70, 120]), prefix_names=True))
+        assert _agree(emu, oracle, _read(p)) == 0
     c1 = emu.path_counts()
+    assert c1[2] > 10, c1                                        # prefix-related names: the full merge sort with name compares
     assert c1[0] - c0[0] > 10 and c1[1] - c0[1] > 2, (c0, c1)   # proper orders took the rank sort, the nested ones fell back
     assert c0[3] > 10 and c1[3] - c0[3] > 10, (c0, c1)           # sections with more than 32 notes went to the whole CTA
     seeds = [variants[k] for k in sorted(variants) if k not in ("c_maxpage_2m", "c_static", "c_static_pie")]
