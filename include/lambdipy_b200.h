@@ -84,6 +84,8 @@ typedef struct lb2_stats {
   float plan_ms;              /* plan + offset scan kernels, CUDA events on the call's stream   */
   float compact_ms;           /* compaction kernel                                              */
   float h2d_ms, d2h_ms;       /* lb2_strip_host only: summed copy time                          */
+  uint64_t h2d_bytes;         /* lb2_strip_host only: bytes that crossed the bus upwards (DMA'd ranges, or what the   */
+  uint64_t d2h_bytes;         /*   kernels pulled in zero-copy mode) and downwards                                    */
 } lb2_stats;
 
 typedef struct lb2_tree_stats {

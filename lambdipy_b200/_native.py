@@ -33,6 +33,7 @@ class Stats(C.Structure):
         ("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("copy_bytes", C.c_uint64), ("header_bytes", C.c_uint64),
         ("n_tiles", C.c_uint64), ("out_bytes_needed", C.c_uint64),
         ("plan_ms", C.c_float), ("compact_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

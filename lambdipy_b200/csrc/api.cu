@@ -42,6 +42,8 @@ struct Workspace {
   uint8_t *d_scratch = nullptr;
   Tile *d_tiles = nullptr;
   BatchCounters *d_ctr = nullptr;
+  UpRange *d_ranges = nullptr, *h_ranges = nullptr;  // host-buffer pipeline: input ranges to upload (pinned copy)
+  uint32_t cap_ranges = 0;
   uint64_t *h_stage = nullptr;  // pinned: 2*(n+1) offsets/sizes up
   uint8_t *h_res = nullptr;     // pinned: out_off[n+1] | out_size[n] | status[n] down (queued behind the kernels)
   BatchCounters *h_ctr = nullptr;
@@ -126,6 +128,8 @@ static void ws_free(Workspace &w) {
   if (w.h_stage) cudaFreeHost(w.h_stage);
   if (w.h_res) cudaFreeHost(w.h_res);
   if (w.h_ctr) cudaFreeHost(w.h_ctr);
+  cudaFree(w.d_ranges);
+  if (w.h_ranges) cudaFreeHost(w.h_ranges);
   for (auto &e : w.ev) if (e) cudaEventDestroy(e);
   if (w.done) cudaEventDestroy(w.done);
   w = Workspace();
@@ -179,7 +183,8 @@ static uint64_t tile_bound(const uint64_t *sizes, uint32_t n) {
 
 // Enqueue plan -> scan -> (compact) for one batch on `s`.  h_off/h_sizes are host arrays.
 static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const uint64_t *h_off, const uint64_t *h_sizes,
-                         uint32_t n, uint8_t *d_out, uint64_t out_cap, uint32_t flags, cudaStream_t s, bool compact) {
+                         uint32_t n, uint8_t *d_out, uint64_t out_cap, uint32_t flags, cudaStream_t s, bool compact,
+                         bool export_ranges = false) {
   for (uint32_t i = 0; i < n; i++)
     if (h_off[i] & 15) { ctx->err = "input offsets must be multiples of 16"; return LB2_E_ARG; }
   // sizes -> staging (pinned), upload
@@ -201,16 +206,27 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
   CK(cudaMemcpyAsync(w.d_in_size, st_size, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(w.d_ctr, 0, sizeof(BatchCounters), s));
   CK(cudaEventRecord(w.ev[0], s));
+  if (export_ranges && w.cap_ranges < 8u * n + 4096u) {
+    cudaFree(w.d_ranges);
+    if (w.h_ranges) cudaFreeHost(w.h_ranges);
+    w.d_ranges = nullptr; w.h_ranges = nullptr; w.cap_ranges = 0;
+    const uint32_t cap = 8u * std::max<uint32_t>(n, w.cap_files) + 4096u;
+    CK(cudaMalloc(&w.d_ranges, (size_t)cap * sizeof(UpRange)));
+    CK(cudaHostAlloc(&w.h_ranges, (size_t)cap * sizeof(UpRange), cudaHostAllocDefault));
+    w.cap_ranges = cap;
+  }
   PlanArgs pa;
   pa.in = d_in; pa.in_off = w.d_in_off; pa.in_size = w.d_in_size; pa.n_files = n; pa.flags = flags;
   pa.scratch = w.d_scratch; pa.out_size = w.d_out_size; pa.status = w.d_status;
   pa.tiles = w.d_tiles; pa.tile_cap = w.cap_tiles; pa.ctr = w.d_ctr;
+  pa.up_ranges = export_ranges ? w.d_ranges : nullptr; pa.up_cap = export_ranges ? w.cap_ranges : 0;
   launch_plan(pa, s);
   launch_scan(w.d_out_size, w.d_out_off, n, compact ? out_cap : ~0ull, w.d_ctr, s);
   CK(cudaEventRecord(w.ev[1], s));
   if (compact) {
     CompactArgs ca;
     ca.tiles = w.d_tiles; ca.ctr = w.d_ctr; ca.out_off = w.d_out_off; ca.out = d_out;
+    ca.rebase_lo = ca.rebase_len = ca.rebase_delta = 0;
     if (ctx->use_tma) launch_compact_tma(ca, ctx->sm_count, s);
     else launch_compact(ca, ctx->sm_count * ctx->compact_ctas_per_sm, s);
   }
@@ -221,6 +237,7 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
     uint64_t *r_off = reinterpret_cast<uint64_t *>(w.h_res), *r_size = r_off + (w.cap_files + 1);
     int32_t *r_status = reinterpret_cast<int32_t *>(r_size + (w.cap_files + 1));
     CK(cudaMemcpyAsync(w.h_ctr, w.d_ctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s));
+    if (export_ranges) CK(cudaMemcpyAsync(w.h_ranges, w.d_ranges, (size_t)std::min<uint32_t>(w.cap_ranges, 8u * n + 4096u) * sizeof(UpRange), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(r_off, w.d_out_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     if (n) {
       CK(cudaMemcpyAsync(r_size, w.d_out_size, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -438,6 +455,10 @@ static uint64_t env_u64(const char *name, uint64_t dflt) {
   return v ? strtoull(v, nullptr, 10) : dflt;
 }
 
+static int strip_host_dma(lb2_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_alias, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                          uint32_t n_files, uint8_t *h_out, uint64_t out_capacity, uint64_t *h_out_off, uint64_t *h_out_sizes,
+                          int32_t *h_status, uint32_t flags, lb2_stats *stats);
+
 int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, const uint64_t *h_in_sizes, uint32_t n_files,
                    void *h_out_v, uint64_t out_capacity, uint64_t *h_out_off, uint64_t *h_out_sizes, int32_t *h_status,
                    uint32_t flags, lb2_stats *stats) {
@@ -458,12 +479,19 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, c
                     cudaHostGetDevicePointer(&d_in_alias, const_cast<uint8_t *>(h_in), 0) == cudaSuccess &&
                     cudaHostGetDevicePointer(&d_out_alias, h_out, 0) == cudaSuccess;
     cudaGetLastError();  // clear "invalid value" from probing pageable memory
+    if (ok && env_u64("LB2_HOST_DMA", 1)) {
+      // default for pinned, mapped arenas: plan over the mapping, copy-engine transfers of the kept ranges
+      return strip_host_dma(ctx, h_in, static_cast<const uint8_t *>(d_in_alias), h_in_off, h_in_sizes, n_files, h_out, out_capacity,
+                            h_out_off, h_out_sizes, h_status, flags, stats);
+    }
     if (ok) {
       int rc = enqueue_batch(ctx, ctx->ws, static_cast<const uint8_t *>(d_in_alias), h_in_off, h_in_sizes, n_files,
                              static_cast<uint8_t *>(d_out_alias), out_capacity, flags, ctx->stream, true);
       if (rc) return rc;
       lb2_stats st;
       rc = collect_batch(ctx, ctx->ws, h_out_off, h_out_sizes, h_status, &st);
+      st.h2d_bytes = st.copy_bytes + st.header_bytes;   // pulled by the kernels through the mapping
+      st.d2h_bytes = st.out_bytes;
       if (stats) *stats = st;
       return rc;
     }
@@ -522,6 +550,7 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, c
     if (out_base + bytes > out_capacity) { ctx->err = "host output arena too small"; total.out_bytes_needed = out_base + bytes; return LB2_E_CAPACITY; }
     CK(cudaEventRecord(sl.ev_d2h[0], sl.stream));
     if (bytes) CK(cudaMemcpyAsync(h_out + out_base, sl.d_out, bytes, cudaMemcpyDeviceToHost, sl.stream));
+    total.d2h_bytes += bytes;
     CK(cudaEventRecord(sl.ev_d2h[1], sl.stream));
     for (uint32_t i = 0; i < n; i++) h_out_off[c.f0 + i] = out_base + coff[i];
     out_base += bytes;
@@ -558,6 +587,7 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, c
     }
     CK(cudaEventRecord(sl.ev_h2d[0], sl.stream));
     CK(cudaMemcpyAsync(sl.d_in, h_in + c.in_base, h_in_off[c.f1] - c.in_base, cudaMemcpyHostToDevice, sl.stream));
+    total.h2d_bytes += h_in_off[c.f1] - c.in_base;
     CK(cudaEventRecord(sl.ev_h2d[1], sl.stream));
     rel_off.resize(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel_off[i] = h_in_off[c.f0 + i] - c.in_base;
@@ -576,6 +606,158 @@ int lb2_strip_host(lb2_ctx *ctx, const void *h_in_v, const uint64_t *h_in_off, c
 }
 
 }  // extern "C"
+
+
+// ---- host buffers, pinned and mapped: plan over the mapping, upload only what is kept, compact in HBM ----------
+// Measured on this box (profiles/r02_pcie_probe.txt): the copy engines move 49.6 GB/s per direction with both
+// directions busy, SM loads/stores on mapped host memory 40.6 (what the zero-copy path gets).  So, per chunk of
+// whole files (<= LB2_CHUNK_MB of arena span, three slots rotating):
+//   1. plan + scan run on the host-mapped input: only headers, names and notes cross the bus; the kernel also
+//      lists the input ranges its copy extents read (small files whole, neighbours merged);
+//   2. those ranges are uploaded by the copy engine into a device slot laid out like the host arena -- dropped
+//      sections (.symtab/.strtab/.debug_*) still never cross the bus;
+//   3. the compaction kernel runs HBM -> HBM (tile sources inside the host mapping are rebased onto the slot);
+//   4. one DMA brings the chunk's output down.
+// The plan of chunk k+1 is queued before the host waits for chunk k's plan results, so the engines stay busy.
+static int strip_host_dma(lb2_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_alias, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
+                          uint32_t n_files, uint8_t *h_out, uint64_t out_capacity, uint64_t *h_out_off, uint64_t *h_out_sizes,
+                          int32_t *h_status, uint32_t flags, lb2_stats *stats) {
+  const uint64_t chunk_bytes = env_u64("LB2_CHUNK_MB", 256) << 20;
+  lb2_stats total;
+  memset(&total, 0, sizeof total);
+  total.n_files = n_files;
+  struct Chunk { uint32_t f0, f1; uint64_t in_base, in_span; };
+  std::vector<Chunk> chunks;
+  for (uint32_t f = 0; f < n_files;) {
+    uint32_t g = f + 1;
+    while (g < n_files && h_in_off[g + 1] - h_in_off[f] <= chunk_bytes) g++;
+    chunks.push_back({f, g, h_in_off[f], ((h_in_off[g] - h_in_off[f]) + 255) & ~255ull});
+    f = g;
+  }
+  const int NS = 3;
+  for (int k = 0; k < NS; k++) {
+    auto &sl = ctx->slot[k];
+    if (!sl.stream) {
+      CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+      for (auto &e : sl.ev_h2d) CK(cudaEventCreate(&e));
+      for (auto &e : sl.ev_d2h) CK(cudaEventCreate(&e));
+      CK(cudaEventCreateWithFlags(&sl.ev_planned, cudaEventDisableTiming));
+    }
+  }
+  uint64_t out_base = 0;
+  std::vector<uint64_t> rel_off, coff;
+  auto plan = [&](size_t ci) -> int {
+    auto &sl = ctx->slot[ci % NS];
+    const Chunk &c = chunks[ci];
+    const uint32_t n = c.f1 - c.f0;
+    if (ci >= (size_t)NS) {  // the slot's previous occupant must be fully downloaded
+      CK(cudaEventSynchronize(sl.ev_d2h[1]));
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, sl.ev_h2d[0], sl.ev_h2d[1]);
+      cudaEventElapsedTime(&b, sl.ev_d2h[0], sl.ev_d2h[1]);
+      total.h2d_ms += a; total.d2h_ms += b;
+    }
+    rel_off.resize(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel_off[i] = h_in_off[c.f0 + i] - c.in_base;
+    return enqueue_batch(ctx, sl.ws, d_in_alias + c.in_base, rel_off.data(), h_in_sizes ? h_in_sizes + c.f0 : nullptr, n, nullptr, 0, flags,
+                         sl.stream, false, true);
+  };
+  auto move = [&](size_t ci) -> int {
+    auto &sl = ctx->slot[ci % NS];
+    const Chunk &c = chunks[ci];
+    const uint32_t n = c.f1 - c.f0;
+    lb2_stats st;
+    coff.resize(n + 1);
+    int r = collect_batch(ctx, sl.ws, coff.data(), h_out_sizes + c.f0, h_status + c.f0, &st);
+    if (r) return r;
+    const uint64_t bytes = coff[n];
+    if (out_base + bytes > out_capacity) { ctx->err = "host output arena too small"; total.out_bytes_needed = out_base + bytes; return LB2_E_CAPACITY; }
+    if (sl.cap_in < c.in_span + 256) {
+      cudaFree(sl.d_in); sl.d_in = nullptr; sl.cap_in = 0;
+      const uint64_t need = std::max<uint64_t>(c.in_span + 256, std::min<uint64_t>(chunk_bytes, 64ull << 20));
+      CK(cudaMalloc(&sl.d_in, need));
+      sl.cap_in = need;
+    }
+    if (sl.cap_out < bytes + 256) {
+      cudaFree(sl.d_out); sl.d_out = nullptr; sl.cap_out = 0;
+      const uint64_t need = std::max<uint64_t>(bytes + (1u << 20), c.in_span + (8u << 20));
+      CK(cudaMalloc(&sl.d_out, need));
+      sl.cap_out = need;
+    }
+    // upload what the copy extents read
+    const BatchCounters &bc = *sl.ws.h_ctr;
+    CK(cudaEventRecord(sl.ev_h2d[0], sl.stream));
+    if (bc.ranges_overflow || bc.n_ranges > sl.ws.cap_ranges) {
+      CK(cudaMemcpyAsync(sl.d_in, h_in + c.in_base, h_in_off[c.f1] - c.in_base, cudaMemcpyHostToDevice, sl.stream));
+      total.h2d_bytes += h_in_off[c.f1] - c.in_base;
+    } else {
+      // the kernel appended the ranges in no particular order: sort, fuse neighbours (files are 256-byte
+      // padded, so runs of small files become one transfer), one DMA per fused range
+      UpRange *rg = sl.ws.h_ranges;
+      std::sort(rg, rg + bc.n_ranges, [](const UpRange &x, const UpRange &y) { return x.off < y.off; });
+      uint64_t rs = 0, re = 0;
+      auto flush = [&]() -> int {
+        if (re <= rs) return LB2_OK;
+        if (re > c.in_span) { ctx->err = "upload range outside the chunk"; return LB2_E_STATE; }
+        CK(cudaMemcpyAsync(sl.d_in + rs, h_in + c.in_base + rs, re - rs, cudaMemcpyHostToDevice, sl.stream));
+        total.h2d_bytes += re - rs;
+        return LB2_OK;
+      };
+      for (uint32_t k = 0; k < bc.n_ranges; k++) {
+        const uint64_t o = rg[k].off, e = rg[k].off + rg[k].len;
+        if (re > rs && o <= re + 8192) { if (e > re) re = e; }
+        else { int fr = flush(); if (fr) return fr; rs = o; re = e; }
+      }
+      int fr = flush();
+      if (fr) return fr;
+    }
+    CK(cudaEventRecord(sl.ev_h2d[1], sl.stream));
+    // compaction on the device copy
+    CompactArgs ca;
+    ca.tiles = sl.ws.d_tiles; ca.ctr = sl.ws.d_ctr; ca.out_off = sl.ws.d_out_off; ca.out = sl.d_out;
+    ca.rebase_lo = reinterpret_cast<uint64_t>(d_in_alias + c.in_base);
+    ca.rebase_len = c.in_span;
+    ca.rebase_delta = reinterpret_cast<uint64_t>(sl.d_in) - ca.rebase_lo;
+    CK(cudaEventRecord(sl.ws.ev[1], sl.stream));
+    if (ctx->use_tma) launch_compact_tma(ca, ctx->sm_count, sl.stream);
+    else launch_compact(ca, ctx->sm_count * ctx->compact_ctas_per_sm, sl.stream);
+    CK(cudaEventRecord(sl.ws.ev[2], sl.stream));
+    CK(cudaEventRecord(sl.ev_d2h[0], sl.stream));
+    if (bytes) CK(cudaMemcpyAsync(h_out + out_base, sl.d_out, bytes, cudaMemcpyDeviceToHost, sl.stream));
+    total.d2h_bytes += bytes;
+    total.h2d_bytes += st.header_bytes;   // what the plan kernel read through the mapping
+    CK(cudaEventRecord(sl.ev_d2h[1], sl.stream));
+    CK(cudaGetLastError());
+    for (uint32_t i = 0; i < n; i++) h_out_off[c.f0 + i] = out_base + coff[i];
+    out_base += bytes;
+    total.n_ok += st.n_ok; total.n_unsupported += st.n_unsupported; total.in_bytes += st.in_bytes; total.out_bytes += st.out_bytes;
+    total.copy_bytes += st.copy_bytes; total.header_bytes += st.header_bytes; total.n_tiles += st.n_tiles;
+    total.plan_ms += st.plan_ms;
+    return LB2_OK;
+  };
+  int rc = LB2_OK;
+  for (size_t ci = 0; ci < chunks.size() && rc == LB2_OK; ci++) {
+    rc = plan(ci);
+    if (rc == LB2_OK && ci >= 1) rc = move(ci - 1);
+  }
+  if (rc == LB2_OK && !chunks.empty()) rc = move(chunks.size() - 1);
+  for (int k = 0; k < NS; k++) {
+    auto &sl = ctx->slot[k];
+    cudaStreamSynchronize(sl.stream);
+    sl.ws.in_flight = false;
+    if ((size_t)k < chunks.size()) {
+      float a = 0, b = 0, cms = 0;
+      if (cudaEventElapsedTime(&a, sl.ev_h2d[0], sl.ev_h2d[1]) == cudaSuccess) total.h2d_ms += a;
+      if (cudaEventElapsedTime(&b, sl.ev_d2h[0], sl.ev_d2h[1]) == cudaSuccess) total.d2h_ms += b;
+      if (cudaEventElapsedTime(&cms, sl.ws.ev[1], sl.ws.ev[2]) == cudaSuccess) total.compact_ms += cms;  // (last chunk of each slot only)
+    }
+  }
+  cudaGetLastError();
+  h_out_off[n_files] = out_base;
+  if (total.out_bytes_needed == 0) total.out_bytes_needed = out_base;
+  if (stats) *stats = total;
+  return rc;
+}
 
 // ---------------------------------------------------------------------------- tree walker
 static bool ends_with(const char *s, const char *suf) {
@@ -1194,6 +1376,7 @@ int lb2_corpus_scatter(lb2_ctx *ctx, void *d_arena, const void *h_data, uint64_t
   CK(cudaMemcpyAsync(d_off, &zero, sizeof zero, cudaMemcpyHostToDevice, s));
   CompactArgs ca;
   ca.tiles = d_tiles; ca.ctr = d_ctr; ca.out_off = d_off; ca.out = static_cast<uint8_t *>(d_arena);
+  ca.rebase_lo = ca.rebase_len = ca.rebase_delta = 0;
   launch_compact(ca, ctx->sm_count * 4, s);
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());

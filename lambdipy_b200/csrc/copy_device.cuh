@@ -90,7 +90,9 @@ __device__ __forceinline__ TileView load_tile(const CompactArgs &a, unsigned lon
   const uint4 *tp = reinterpret_cast<const uint4 *>(a.tiles + t);
   const uint4 q0 = __ldg(tp), q1 = __ldg(tp + 1);
   TileView v;
-  v.src = reinterpret_cast<const uint8_t *>((uint64_t)q0.x | ((uint64_t)q0.y << 32));
+  uint64_t src = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
+  if (src - a.rebase_lo < a.rebase_len) src += a.rebase_delta;
+  v.src = reinterpret_cast<const uint8_t *>(src);
   v.dst = a.out + __ldg(a.out_off + q1.y) + ((uint64_t)q0.z | ((uint64_t)q0.w << 32));
   v.len = q1.x;
   return v;

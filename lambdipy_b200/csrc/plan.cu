@@ -1676,6 +1676,27 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
   }
   __syncthreads();
   if (sm.fail) LB2_REJECT(sm.fail);
+  if (a.up_ranges && tid == 0) {
+    // host-buffer pipeline: which parts of this file have to cross the bus.  Small files go whole (one DMA);
+    // otherwise the input-arena sources of the copy extents, in output order, neighbours closer than 4 KB merged.
+    auto push = [&](uint64_t off, uint64_t len) {
+      const unsigned int at = atomicAdd(&a.ctr->n_ranges, 1u);
+      if (at < a.up_cap) { a.up_ranges[at].off = off; a.up_ranges[at].len = len; }
+      else a.ctr->ranges_overflow = 1;
+    };
+    if (n <= 65536) push(base, n);
+    else {
+      const uint64_t lo = reinterpret_cast<uint64_t>(in), hi = lo + n;
+      uint64_t rs = 0, re = 0;
+      for (int e = 0; e < sm.n_ext; e++) {
+        const uint64_t s0 = sm.u.x.src[e], l0 = sm.u.x.len[e];
+        if (s0 < lo || s0 >= hi || l0 == 0) continue;   // zero fill or regenerated table
+        if (re && s0 >= rs && s0 <= re + 4096) { if (s0 + l0 > re) re = s0 + l0; }
+        else { if (re) push(base + (rs - lo), re - rs); rs = s0; re = s0 + l0; }
+      }
+      if (re) push(base + (rs - lo), re - rs);
+    }
+  }
 
   LB2_T(8);
   // ---- M. tiles: small extents go one per warp, big ones are written by the whole CTA

@@ -107,7 +107,7 @@ extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8
   memset(&ctr, 0, sizeof ctr);
   PlanArgs a;
   a.in = arena; a.in_off = &in_off; a.in_size = &in_size; a.n_files = 1; a.flags = flags;
-  a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr;
+  a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr; a.up_ranges = nullptr; a.up_cap = 0;
   run_block(a);
   int rc = status;
   if (status == ST_OK && !ctr.overflow) {

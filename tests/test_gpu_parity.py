@@ -156,13 +156,20 @@ def test_real_torch_config3(gpu_ctx, oracle, tmp_path):
 def test_chunked_pipeline_matches_single_chunk(gpu_ctx, variants, monkeypatch):
     """The host pipeline splits batches into chunks; results must not depend on the split."""
     from lambdipy_b200 import strip as S
-    blobs = [_read(variants[k]) for k in sorted(variants)] * 3
-    a, sa, _ = S.strip_buffers(gpu_ctx, blobs)          # default: zero-copy over mapped pinned arenas
+    blobs = ([_read(variants[k]) for k in sorted(variants)] + [_read(p) for p in F.real_corpus("small")]) * 3
+    a, sa, sta = S.strip_buffers(gpu_ctx, blobs)        # default: plan over the mapped arena, DMA of the kept ranges, compaction in HBM
+    assert sta["h2d_ms"] > 0 and sta["d2h_ms"] > 0
+    monkeypatch.setenv("LB2_CHUNK_MB", "1")              # the same with ~1 MB chunks: many slots in flight
+    a1, sa1, _ = S.strip_buffers(gpu_ctx, blobs)
+    monkeypatch.delenv("LB2_CHUNK_MB")
+    monkeypatch.setenv("LB2_HOST_DMA", "0")
+    z, sz, stz = S.strip_buffers(gpu_ctx, blobs)        # zero-copy: kernels read and write the mapped pinned arenas directly
+    assert stz["h2d_ms"] == 0
     monkeypatch.setenv("LB2_HOST_ZEROCOPY", "0")
-    b, sb, stb = S.strip_buffers(gpu_ctx, blobs)        # staged: H2D -> kernels -> D2H in 256 MB chunks
+    b, sb, stb = S.strip_buffers(gpu_ctx, blobs)        # staged: H2D of whole files -> kernels -> D2H in 256 MB chunks
     monkeypatch.setenv("LB2_CHUNK_MB", "0")              # staged, every file its own chunk
     c, sc, _ = S.strip_buffers(gpu_ctx, blobs)
-    assert sa == sb == sc and a == b == c
+    assert sa == sa1 == sz == sb == sc and a == a1 == z == b == c
     assert stb["h2d_ms"] > 0
 
 
