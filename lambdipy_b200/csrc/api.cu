@@ -118,6 +118,27 @@ struct NumaPreferred {
   ~NumaPreferred() { if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0); }
 };
 
+// Control data of a batch (offsets up; counters, sizes, status, upload ranges down) normally rides on small
+// cudaMemcpyAsync calls.  In the host-buffer DMA pipeline those would queue on the copy engines behind 100 MB
+// transfers of the neighbouring chunks and stall the host for milliseconds, so there the kernels read the
+// offsets through the mapping of the pinned staging buffer and this kernel stores the results into mapped
+// pinned memory with ordinary SM stores: no copy engine involved.
+__global__ void lb2_zero_ctr_kernel(BatchCounters *ctr) {
+  if (threadIdx.x < sizeof(BatchCounters) / 4) reinterpret_cast<uint32_t *>(ctr)[threadIdx.x] = 0;
+}
+__global__ void __launch_bounds__(256) lb2_publish_kernel(const BatchCounters *ctr, const uint64_t *out_off, const uint64_t *out_size,
+                                                          const int32_t *status, const UpRange *ranges, uint32_t n, uint32_t range_cap,
+                                                          BatchCounters *h_ctr, uint64_t *h_off, uint64_t *h_size, int32_t *h_status, UpRange *h_ranges) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  if (t < sizeof(BatchCounters) / 4) reinterpret_cast<uint32_t *>(h_ctr)[t] = reinterpret_cast<const uint32_t *>(ctr)[t];
+  for (uint32_t i = t; i <= n; i += stride) h_off[i] = out_off[i];
+  for (uint32_t i = t; i < n; i += stride) { h_size[i] = out_size[i]; h_status[i] = status[i]; }
+  if (ranges) {
+    const uint32_t nr = ctr->n_ranges < range_cap ? ctr->n_ranges : range_cap;
+    for (uint32_t i = t; i < nr; i += stride) h_ranges[i] = ranges[i];
+  }
+}
+
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -138,7 +159,7 @@ static void ws_free(Workspace &w) {
 static int ws_reserve(lb2_ctx *ctx, Workspace &w, uint32_t n_files, uint64_t n_tiles) {
   if (!w.d_ctr) {
     CK(cudaMalloc(&w.d_ctr, sizeof(BatchCounters)));
-    CK(cudaHostAlloc(&w.h_ctr, sizeof(BatchCounters) + 64, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&w.h_ctr, sizeof(BatchCounters) + 64, cudaHostAllocMapped));
     for (auto &e : w.ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   }
@@ -157,8 +178,8 @@ static int ws_reserve(lb2_ctx *ctx, Workspace &w, uint32_t n_files, uint64_t n_t
     CK(cudaMalloc(&w.d_out_off, (cap + 1) * sizeof(uint64_t)));
     CK(cudaMalloc(&w.d_status, (cap + 1) * sizeof(int32_t)));
     CK(cudaMalloc(&w.d_scratch, (uint64_t)cap * SCR_STRIDE));
-    CK(cudaHostAlloc(&w.h_stage, (2ull * cap + 2) * sizeof(uint64_t), cudaHostAllocDefault));
-    CK(cudaHostAlloc(&w.h_res, (2ull * cap + 2) * sizeof(uint64_t) + (cap + 1ull) * sizeof(int32_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&w.h_stage, (2ull * cap + 2) * sizeof(uint64_t), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&w.h_res, (2ull * cap + 2) * sizeof(uint64_t) + (cap + 1ull) * sizeof(int32_t), cudaHostAllocMapped));
     w.cap_files = cap;
   }
   if (n_tiles > w.cap_tiles) {
@@ -184,7 +205,7 @@ static uint64_t tile_bound(const uint64_t *sizes, uint32_t n) {
 // Enqueue plan -> scan -> (compact) for one batch on `s`.  h_off/h_sizes are host arrays.
 static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const uint64_t *h_off, const uint64_t *h_sizes,
                          uint32_t n, uint8_t *d_out, uint64_t out_cap, uint32_t flags, cudaStream_t s, bool compact,
-                         bool export_ranges = false) {
+                         bool export_ranges = false, bool via_mapping = false) {
   for (uint32_t i = 0; i < n; i++)
     if (h_off[i] & 15) { ctx->err = "input offsets must be multiples of 16"; return LB2_E_ARG; }
   // sizes -> staging (pinned), upload
@@ -202,9 +223,18 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
   st_size = w.h_stage + (w.cap_files + 1);
   memcpy(st_off, h_off, (size_t)n * sizeof(uint64_t));
   memcpy(st_size, tmp.data(), (size_t)n * sizeof(uint64_t));
-  CK(cudaMemcpyAsync(w.d_in_off, st_off, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(w.d_in_size, st_size, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(w.d_ctr, 0, sizeof(BatchCounters), s));
+  const uint64_t *k_in_off = w.d_in_off, *k_in_size = w.d_in_size;
+  if (via_mapping) {  // no copy-engine traffic for control data (see lb2_publish_kernel)
+    void *alias = nullptr;
+    CK(cudaHostGetDevicePointer(&alias, w.h_stage, 0));
+    k_in_off = static_cast<const uint64_t *>(alias);
+    k_in_size = k_in_off + (w.cap_files + 1);
+    lb2_zero_ctr_kernel<<<1, 64, 0, s>>>(w.d_ctr);
+  } else {
+    CK(cudaMemcpyAsync(w.d_in_off, st_off, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.d_in_size, st_size, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(w.d_ctr, 0, sizeof(BatchCounters), s));
+  }
   CK(cudaEventRecord(w.ev[0], s));
   if (export_ranges && w.cap_ranges < 8u * n + 4096u) {
     cudaFree(w.d_ranges);
@@ -212,11 +242,11 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
     w.d_ranges = nullptr; w.h_ranges = nullptr; w.cap_ranges = 0;
     const uint32_t cap = 8u * std::max<uint32_t>(n, w.cap_files) + 4096u;
     CK(cudaMalloc(&w.d_ranges, (size_t)cap * sizeof(UpRange)));
-    CK(cudaHostAlloc(&w.h_ranges, (size_t)cap * sizeof(UpRange), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&w.h_ranges, (size_t)cap * sizeof(UpRange), cudaHostAllocMapped));
     w.cap_ranges = cap;
   }
   PlanArgs pa;
-  pa.in = d_in; pa.in_off = w.d_in_off; pa.in_size = w.d_in_size; pa.n_files = n; pa.flags = flags;
+  pa.in = d_in; pa.in_off = k_in_off; pa.in_size = k_in_size; pa.n_files = n; pa.flags = flags;
   pa.scratch = w.d_scratch; pa.out_size = w.d_out_size; pa.status = w.d_status;
   pa.tiles = w.d_tiles; pa.tile_cap = w.cap_tiles; pa.ctr = w.d_ctr;
   pa.up_ranges = export_ranges ? w.d_ranges : nullptr; pa.up_cap = export_ranges ? w.cap_ranges : 0;
@@ -236,12 +266,24 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
   {
     uint64_t *r_off = reinterpret_cast<uint64_t *>(w.h_res), *r_size = r_off + (w.cap_files + 1);
     int32_t *r_status = reinterpret_cast<int32_t *>(r_size + (w.cap_files + 1));
-    CK(cudaMemcpyAsync(w.h_ctr, w.d_ctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s));
-    if (export_ranges) CK(cudaMemcpyAsync(w.h_ranges, w.d_ranges, (size_t)std::min<uint32_t>(w.cap_ranges, 8u * n + 4096u) * sizeof(UpRange), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(r_off, w.d_out_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    if (n) {
-      CK(cudaMemcpyAsync(r_size, w.d_out_size, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(r_status, w.d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (via_mapping) {
+      void *a_ctr = nullptr, *a_res = nullptr, *a_rng = nullptr;
+      CK(cudaHostGetDevicePointer(&a_ctr, w.h_ctr, 0));
+      CK(cudaHostGetDevicePointer(&a_res, w.h_res, 0));
+      if (export_ranges) CK(cudaHostGetDevicePointer(&a_rng, w.h_ranges, 0));
+      uint64_t *m_off = static_cast<uint64_t *>(a_res), *m_size = m_off + (w.cap_files + 1);
+      int32_t *m_status = reinterpret_cast<int32_t *>(m_size + (w.cap_files + 1));
+      lb2_publish_kernel<<<std::max(1u, std::min(32u, (n + 255u) / 256u)), 256, 0, s>>>(
+          w.d_ctr, w.d_out_off, w.d_out_size, w.d_status, export_ranges ? w.d_ranges : nullptr, n, w.cap_ranges,
+          static_cast<BatchCounters *>(a_ctr), m_off, m_size, m_status, static_cast<UpRange *>(a_rng));
+    } else {
+      CK(cudaMemcpyAsync(w.h_ctr, w.d_ctr, sizeof(BatchCounters), cudaMemcpyDeviceToHost, s));
+      if (export_ranges) CK(cudaMemcpyAsync(w.h_ranges, w.d_ranges, (size_t)std::min<uint32_t>(w.cap_ranges, 8u * n + 4096u) * sizeof(UpRange), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(r_off, w.d_out_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      if (n) {
+        CK(cudaMemcpyAsync(r_size, w.d_out_size, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(r_status, w.d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      }
     }
     CK(cudaEventRecord(w.done, s));
   }
@@ -660,7 +702,7 @@ static int strip_host_dma(lb2_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in
     rel_off.resize(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel_off[i] = h_in_off[c.f0 + i] - c.in_base;
     return enqueue_batch(ctx, sl.ws, d_in_alias + c.in_base, rel_off.data(), h_in_sizes ? h_in_sizes + c.f0 : nullptr, n, nullptr, 0, flags,
-                         sl.stream, false, true);
+                         sl.stream, false, true, true);
   };
   auto move = [&](size_t ci) -> int {
     auto &sl = ctx->slot[ci % NS];
