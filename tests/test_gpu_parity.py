@@ -157,14 +157,15 @@ def test_chunked_pipeline_matches_single_chunk(gpu_ctx, variants, monkeypatch):
     """The host pipeline splits batches into chunks; results must not depend on the split."""
     from lambdipy_b200 import strip as S
     blobs = ([_read(variants[k]) for k in sorted(variants)] + [_read(p) for p in F.real_corpus("small")]) * 3
-    a, sa, sta = S.strip_buffers(gpu_ctx, blobs)        # default: plan over the mapped arena, DMA of the kept ranges, compaction in HBM
-    assert sta["h2d_ms"] > 0 and sta["d2h_ms"] > 0
+    z, sz, stz = S.strip_buffers(gpu_ctx, blobs)        # default: zero-copy, kernels read and write the mapped pinned arenas directly
+    assert stz["h2d_ms"] == 0 and stz["h2d_bytes"] == stz["copy_bytes"] + stz["header_bytes"] and stz["d2h_bytes"] == stz["out_bytes"]
+    monkeypatch.setenv("LB2_HOST_DMA", "1")
+    a, sa, sta = S.strip_buffers(gpu_ctx, blobs)        # plan over the mapped arena, DMA of the kept ranges, compaction in HBM
+    assert sta["h2d_ms"] > 0 and sta["d2h_ms"] > 0 and sta["d2h_bytes"] >= sta["out_bytes"] and 0 < sta["h2d_bytes"] < sum(len(b) for b in blobs)
     monkeypatch.setenv("LB2_CHUNK_MB", "1")              # the same with ~1 MB chunks: many slots in flight
     a1, sa1, _ = S.strip_buffers(gpu_ctx, blobs)
     monkeypatch.delenv("LB2_CHUNK_MB")
     monkeypatch.setenv("LB2_HOST_DMA", "0")
-    z, sz, stz = S.strip_buffers(gpu_ctx, blobs)        # zero-copy: kernels read and write the mapped pinned arenas directly
-    assert stz["h2d_ms"] == 0
     monkeypatch.setenv("LB2_HOST_ZEROCOPY", "0")
     b, sb, stb = S.strip_buffers(gpu_ctx, blobs)        # staged: H2D of whole files -> kernels -> D2H in 256 MB chunks
     monkeypatch.setenv("LB2_CHUNK_MB", "0")              # staged, every file its own chunk
