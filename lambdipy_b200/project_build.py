@@ -59,17 +59,36 @@ class _Warmup:
     longer than stripping a small tree.  It does not depend on the tree, so it runs on a helper
     thread while the reference's script is busy with pip / rm (project_build.py:266-274)."""
 
-    def __init__(self, device):
-        self.device, self.ctx, self.error = device, None, None
+    def __init__(self, device, build_directory=None):
+        self.device, self.ctx, self.error, self.build_directory = device, None, None, build_directory
+        self.prepared = False
         self.thread = threading.Thread(target=self._run, name="lambdipy-b200-warmup", daemon=True)
         self.thread.start()
+
+    @staticmethod
+    def _so_bytes(build_directory):
+        total = 0
+        for d, _, fs in os.walk(build_directory):
+            for f in fs:
+                if f.endswith(".so"):
+                    try:
+                        total += os.path.getsize(os.path.join(d, f))
+                    except OSError:
+                        pass
+        return total
+
+    def _prepare(self, build_directory):
+        # size the pinned slot ring for what is already in the tree (prebuilt packages are copied in before this step,
+        # project_build.py:169-175); pip may add more, the ring is only a staging area
+        if self.ctx is not None and not self.prepared and build_directory and os.path.isdir(build_directory):
+            self.ctx.check(self.ctx.lib.lb2_tree_prepare(self.ctx.h, max(self._so_bytes(build_directory), 1 << 24)))
+            self.prepared = True
 
     def _run(self):
         try:
             from . import _native as N
-            ctx = N.Context(self.device)
-            ctx.check(ctx.lib.lb2_tree_prepare(ctx.h, 0))
-            self.ctx = ctx
+            self.ctx = N.Context(self.device)
+            self._prepare(self.build_directory)
         except BaseException as e:  # re-raised on the caller's thread by result()
             self.error = e
 
@@ -83,11 +102,11 @@ class _Warmup:
 _warm = None
 
 
-def warmup(backend=None):
+def warmup(backend=None, build_directory=None):
     """Start (once) creating the CUDA context in the background; no-op for the gnu/off backends."""
     global _warm
     if _backend(backend) == "b200" and _warm is None:
-        _warm = _Warmup(int(os.environ.get("LAMBDIPY_B200_DEVICE", "0")))
+        _warm = _Warmup(int(os.environ.get("LAMBDIPY_B200_DEVICE", "0")), build_directory)
     return _warm
 
 
@@ -132,7 +151,7 @@ def bundle_report(build_directory):
 def install_non_resolved_requirements(resolved_requirements, requirements, python_version, keep_tests=None, no_docker=False,
                                       build_directory='./build'):
     backend = _backend()
-    warmup(backend)  # the context comes up while the script below runs
+    warmup(backend, build_directory)  # the context comes up while the script below runs
     install_dir = build_directory if no_docker else '/tmp/export'
     pending = [r['line'] for r in requirements if resolved_requirements[r['requirement'].name] is None]
     pip_args = ''.join(' "%s"' % line for line in pending)
