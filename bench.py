@@ -668,9 +668,11 @@ def run_b200(a, rank, local_rank, world):
         dist.destroy_process_group()
     if rank == 0:
         if dist:
-            time.sleep(1.5)  # the other ranks' NCCL shutdown lines: the JSON line is the last thing on stdout
+            time.sleep(1.5)  # let the other ranks' NCCL shutdown lines out first: the JSON line is the last thing on stdout
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
+        if dist:
+            os._exit(0)      # NCCL logs another INFO line from a library destructor at interpreter exit; everything is released
     return 0
 
 
