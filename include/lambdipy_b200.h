@@ -128,10 +128,12 @@ int lb2_memset_d(lb2_ctx *ctx, void *d_dst, int value, uint64_t bytes);
  * multiples of 16 and h_in_sizes[f] gives the exact byte length (NULL: use the offset difference).
  * d_out: output arena of out_capacity bytes; file f lands at out_off[f] (multiples of 256).
  * Enqueues upload of the offsets, the plan kernel, the offset scan and the compaction kernel on
- * `stream` (a cudaStream_t; NULL = the context's own stream) and returns without synchronising. */
+ * `stream` (a cudaStream_t; NULL = the context's own stream) and returns without synchronising.  Up to TWO
+ * batches may be in flight (the second is queued behind the first on the stream, so the GPU does not idle while the
+ * host collects); lb2_batch_results collects them in order.  Batches that share an output arena overwrite it. */
 int lb2_strip_device_async(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes,
                            uint32_t n_files, void *d_out, uint64_t out_capacity, uint32_t flags, void *stream);
-/* Waits for the batch, copies offsets/status back.  Any pointer may be NULL. */
+/* Waits for the OLDEST batch in flight, copies its offsets/status back.  Any pointer may be NULL. */
 int lb2_batch_results(lb2_ctx *ctx, uint64_t *h_out_off /* n+1 */, uint64_t *h_out_sizes /* n */,
                       int32_t *h_status /* n */, lb2_stats *stats);
 

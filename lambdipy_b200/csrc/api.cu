@@ -65,6 +65,7 @@ struct lb2_ctx {
   cudaStream_t stream = nullptr;
   Workspace ws;               // lb2_strip_device_async / lb2_plan_device / even chunks of lb2_strip_device_chunked
   Workspace ws2;              // odd chunks (chunk k+1 is queued before chunk k is collected)
+  int async_head = 0, async_count = 0;  // lb2_strip_device_async: up to two batches in flight (ws, ws2), collected in order
   std::string err;
   int compact_ctas_per_sm = 4;
   int use_tma = 1;             // bulk-copy engine kernel (0.97 of copy peak) ; LB2_COMPACT_TMA=0 selects the LSU kernel (0.90)
@@ -401,20 +402,29 @@ int lb2_strip_device_async(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_
                            uint32_t n_files, void *d_out, uint64_t out_capacity, uint32_t flags, void *stream) {
   if (!ctx || !d_in || !h_in_off || !d_out) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
   CK(cudaSetDevice(ctx->device));
+  if (ctx->async_count >= 2) { ctx->err = "two batches already in flight: collect one with lb2_batch_results first"; return LB2_E_STATE; }
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-  return enqueue_batch(ctx, ctx->ws, static_cast<const uint8_t *>(d_in), h_in_off, h_in_sizes, n_files,
-                       static_cast<uint8_t *>(d_out), out_capacity, flags, s, true);
+  Workspace &w = ((ctx->async_head + ctx->async_count) & 1) ? ctx->ws2 : ctx->ws;
+  int rc = enqueue_batch(ctx, w, static_cast<const uint8_t *>(d_in), h_in_off, h_in_sizes, n_files,
+                         static_cast<uint8_t *>(d_out), out_capacity, flags, s, true);
+  if (rc == LB2_OK) ctx->async_count++;
+  return rc;
 }
 
 int lb2_batch_results(lb2_ctx *ctx, uint64_t *h_out_off, uint64_t *h_out_sizes, int32_t *h_status, lb2_stats *stats) {
   if (!ctx) return LB2_E_ARG;
-  return collect_batch(ctx, ctx->ws, h_out_off, h_out_sizes, h_status, stats);
+  if (ctx->async_count == 0) { ctx->err = "no batch in flight"; return LB2_E_STATE; }
+  Workspace &w = (ctx->async_head & 1) ? ctx->ws2 : ctx->ws;
+  ctx->async_head ^= 1;
+  ctx->async_count--;
+  return collect_batch(ctx, w, h_out_off, h_out_sizes, h_status, stats);
 }
 
 int lb2_plan_device(lb2_ctx *ctx, const void *d_in, const uint64_t *h_in_off, const uint64_t *h_in_sizes, uint32_t n_files,
                     uint32_t flags, uint64_t *h_out_sizes, int32_t *h_status, lb2_stats *stats) {
   if (!ctx || !d_in || !h_in_off) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
   CK(cudaSetDevice(ctx->device));
+  if (ctx->async_count) { ctx->err = "batches of lb2_strip_device_async still in flight"; return LB2_E_STATE; }
   int rc = enqueue_batch(ctx, ctx->ws, static_cast<const uint8_t *>(d_in), h_in_off, h_in_sizes, n_files, nullptr, 0, flags,
                          ctx->stream, false);
   if (rc) return rc;
@@ -431,6 +441,7 @@ int lb2_strip_device_chunked(lb2_ctx *ctx, const void *d_in, const uint64_t *h_i
                              void *d_out_ring, uint64_t slot_capacity, uint64_t max_chunk_bytes, uint32_t flags, void *stream,
                              lb2_chunk_fn on_chunk, void *user, uint64_t *h_out_sizes, int32_t *h_status, lb2_stats *total_out) {
   if (!ctx || !d_in || !h_in_off || !d_out_ring || !slot_capacity) { if (ctx) ctx->err = "NULL argument"; return LB2_E_ARG; }
+  if (ctx->async_count) { ctx->err = "batches of lb2_strip_device_async still in flight"; return LB2_E_STATE; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
   if (!max_chunk_bytes || max_chunk_bytes > slot_capacity) max_chunk_bytes = slot_capacity;

@@ -138,6 +138,33 @@ def test_chunked_device_api_equals_one_batch(gpu_ctx, oracle):
         whole.close(); ring.close()
 
 
+def test_two_batches_in_flight(gpu_ctx, variants):
+    """lb2_strip_device_async accepts a second batch before the first is collected (results come back in order); a third
+    is refused, and so are the calls that need the workspaces for themselves."""
+    from lambdipy_b200 import _native as N
+    from lambdipy_b200.device import DeviceBatch
+    blobs = [open(variants[k], "rb").read() for k in sorted(variants) if k != "c_many_sections"]
+    b = DeviceBatch.from_blobs(gpu_ctx, blobs)
+    try:
+        b.strip_async()
+        ref = b.results()
+        want = [b.read_output(i) for i in range(len(blobs))]
+        b.strip_async()
+        b.strip_async(flags=N.F_NO_MERGE_NOTES)
+        with pytest.raises(N.NativeError) as e:
+            b.strip_async()
+        assert e.value.code == N.LB2_E_STATE
+        first = b.results()
+        second = b.results()
+        assert first["n_ok"] == second["n_ok"] == ref["n_ok"] == len(blobs) and first["out_bytes"] == ref["out_bytes"]
+        with pytest.raises(N.NativeError):
+            b.results()
+        b.strip_async()
+        assert b.results()["out_bytes"] == ref["out_bytes"] and [b.read_output(i) for i in range(len(blobs))] == want
+    finally:
+        b.close()
+
+
 def test_output_capacity_error_is_reported(gpu_ctx, variants):
     from lambdipy_b200 import _native as N
     from lambdipy_b200.device import DeviceBatch
