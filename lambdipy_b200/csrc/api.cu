@@ -43,6 +43,8 @@ struct Workspace {
   Tile *d_tiles = nullptr;
   BatchCounters *d_ctr = nullptr;
   UpRange *d_ranges = nullptr, *h_ranges = nullptr;  // host-buffer pipeline: input ranges to upload (pinned copy)
+  BigExt *d_big = nullptr;      // extents handed to lb2_expand_kernel
+  uint32_t cap_big = 0;
   uint32_t cap_ranges = 0;
   uint64_t *h_stage = nullptr;  // pinned: 2*(n+1) offsets/sizes up
   uint8_t *h_res = nullptr;     // pinned: out_off[n+1] | out_size[n] | status[n] down (queued behind the kernels)
@@ -151,6 +153,7 @@ static void ws_free(Workspace &w) {
   if (w.h_res) cudaFreeHost(w.h_res);
   if (w.h_ctr) cudaFreeHost(w.h_ctr);
   cudaFree(w.d_ranges);
+  cudaFree(w.d_big);
   if (w.h_ranges) cudaFreeHost(w.h_ranges);
   for (auto &e : w.ev) if (e) cudaEventDestroy(e);
   if (w.done) cudaEventDestroy(w.done);
@@ -251,7 +254,16 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
   pa.scratch = w.d_scratch; pa.out_size = w.d_out_size; pa.status = w.d_status;
   pa.tiles = w.d_tiles; pa.tile_cap = w.cap_tiles; pa.ctr = w.d_ctr;
   pa.up_ranges = export_ranges ? w.d_ranges : nullptr; pa.up_cap = export_ranges ? w.cap_ranges : 0;
+  if (w.cap_big < 4u * n + 1024u) {
+    cudaFree(w.d_big);
+    w.d_big = nullptr; w.cap_big = 0;
+    const uint32_t cap = 4u * std::max<uint32_t>(n, w.cap_files) + 1024u;
+    CK(cudaMalloc(&w.d_big, (size_t)cap * sizeof(BigExt)));
+    w.cap_big = cap;
+  }
+  pa.big = w.d_big; pa.big_cap = w.cap_big;
   launch_plan(pa, s);
+  launch_expand(w.d_big, w.cap_big, w.d_ctr, w.d_tiles, ctx->sm_count * 4, s);
   launch_scan(w.d_out_size, w.d_out_off, n, compact ? out_cap : ~0ull, w.d_ctr, s);
   CK(cudaEventRecord(w.ev[1], s));
   if (compact) {

@@ -76,7 +76,6 @@ struct PlanSmem {
   uint8_t ent_pos[MAX_SH + 1];    // position of each entry in the sorted order
   uint8_t sec_ent[MAX_SH];
   int8_t seg[MAX_SH];
-  uint8_t keep[MAX_SH];
   uint8_t new_index[MAX_SH];
   uint8_t order[MAX_SH + 1];
   uint8_t pkeep[MAX_PH];
@@ -100,6 +99,8 @@ struct PlanSmem {
   uint64_t cur, shstr_off, new_shoff, total, hdr_bytes, note_hdr_bytes, copy_bytes;
   unsigned long long tile_base;
   unsigned long long big_ext[3];  // bit e: extent e has more than 64 tiles (MAX_EXT = 140 extents)
+  unsigned long long vbig_ext[3]; // ... more than BIG_EXT_TILES tiles
+  int vbig_taken;                 // the expand kernel's list had room: the CTA does not write those tiles itself
   uint32_t n_tiles;
 #ifdef LB2_PLAN_TIMING
   long long t_warp[4];
@@ -988,7 +989,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       }
       if (err_mal) sm.err_mal = 1;
       if (err_uns) sm.err_uns = 1;
-      sm.keep[i] = (uint8_t)is_keep;
     }
     // the three masks every later phase works from: kept, kept+alloc, kept+NOBITS
     const unsigned mk = __ballot_sync(0xffffffffu, is_keep), ma = __ballot_sync(0xffffffffu, is_keep && is_alloc),
@@ -1622,7 +1622,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     ExtWork &x = sm.u.x;
     int ne = 0, bad = 0;
     unsigned long long big0 = 0, big1 = 0, big2 = 0;   // extents with > 64 tiles (bit = extent index, MAX_EXT = 140)
-    auto mark_big = [&](int at) { if (at < 64) big0 |= 1ull << at; else if (at < 128) big1 |= 1ull << (at - 64); else big2 |= 1ull << (at - 128); };
+    unsigned long long vb0 = 0, vb1 = 0, vb2 = 0;      // ... of which more than BIG_EXT_TILES: candidates for the expand kernel
+    auto mark_big = [&](int at, uint32_t c) {
+      if (at < 64) big0 |= 1ull << at; else if (at < 128) big1 |= 1ull << (at - 64); else big2 |= 1ull << (at - 128);
+      if (c > BIG_EXT_TILES) { if (at < 64) vb0 |= 1ull << at; else if (at < 128) vb1 |= 1ull << (at - 64); else vb2 |= 1ull << (at - 128); }
+    };
     unsigned long long copy_bytes = 0;
     uint32_t running = 0;
     for (int q0 = 0; q0 < total_pieces; q0 += 32) {
@@ -1649,11 +1653,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
         uint32_t t0 = running + inc - (cnt_gap + cnt);
         if (gap) {  // file hole
           x.src[at] = 0; x.dst[at] = prev_end; x.len[at] = dst - prev_end; x.tiles[at] = t0; t0 += cnt_gap;
-          if (cnt_gap > 64) mark_big(at);
+          if (cnt_gap > 64) mark_big(at, cnt_gap);
           at++;
         }
         x.src[at] = src; x.dst[at] = dst; x.len[at] = len; x.tiles[at] = t0;
-        if (cnt > 64) mark_big(at);
+        if (cnt > 64) mark_big(at, cnt);
         copy_bytes += len;
       }
       running += __shfl_sync(0xffffffffu, inc, 31);
@@ -1666,10 +1670,14 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       big0 |= __shfl_xor_sync(0xffffffffu, big0, o);
       big1 |= __shfl_xor_sync(0xffffffffu, big1, o);
       big2 |= __shfl_xor_sync(0xffffffffu, big2, o);
+      vb0 |= __shfl_xor_sync(0xffffffffu, vb0, o);
+      vb1 |= __shfl_xor_sync(0xffffffffu, vb1, o);
+      vb2 |= __shfl_xor_sync(0xffffffffu, vb2, o);
     }
     const bool any_bad = __ballot_sync(0xffffffffu, bad) != 0;
     if (lane == 0) {
       sm.n_ext = ne; sm.copy_bytes = copy_bytes; sm.n_tiles = running; sm.big_ext[0] = big0; sm.big_ext[1] = big1; sm.big_ext[2] = big2;
+      sm.vbig_ext[0] = vb0; sm.vbig_ext[1] = vb1; sm.vbig_ext[2] = vb2; sm.vbig_taken = 0;
       if (any_bad) sm.fail = ST_UNSUPPORTED_LAYOUT;
       else sm.tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);   // one atomicAdd per file reserves the range
     }
@@ -1736,6 +1744,28 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       out[k] = t;
     }
   };
+  // extents with more than BIG_EXT_TILES tiles are only recorded: the expand kernel writes their descriptors with the
+  // whole grid (if its list is full the CTA writes them itself, as it does the other big ones)
+  if (a.big && (sm.vbig_ext[0] | sm.vbig_ext[1] | sm.vbig_ext[2])) {
+    if (tid == 0) {
+      const unsigned nvb = __popcll(sm.vbig_ext[0]) + __popcll(sm.vbig_ext[1]) + __popcll(sm.vbig_ext[2]);
+      const unsigned at0 = atomicAdd(&a.ctr->n_big, nvb);
+      if (at0 + nvb <= a.big_cap) {
+        unsigned at = at0;
+        for (int w = 0; w < 3; w++)
+          for (unsigned long long m = sm.vbig_ext[w]; m; m &= m - 1) {
+            const int e = 64 * w + __ffsll((long long)m) - 1;
+            BigExt r;
+            r.src = sm.u.x.src[e]; r.dst = sm.u.x.dst[e]; r.len = sm.u.x.len[e];
+            r.tile_index = tile_base + sm.u.x.tiles[e]; r.file = f; r.pad = 0;
+            a.big[at++] = r;
+          }
+        sm.vbig_taken = 1;
+      }
+    }
+    __syncthreads();
+  }
+  const bool handed_over = sm.vbig_taken != 0;
   // small extents: one per warp (a thread only looks at its warp's share of the list); the few extents
   // with hundreds of tiles were set aside by phase L and are written by the whole CTA
   const unsigned long long big0 = sm.big_ext[0], big1 = sm.big_ext[1], big2 = sm.big_ext[2];
@@ -1743,9 +1773,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     const bool big = ((e < 64 ? big0 >> e : (e < 128 ? big1 >> (e - 64) : big2 >> (e - 128))) & 1) != 0;
     if (!big) emit_tiles(e, lane, 32);
   }
-  for (unsigned long long m = big0; m; m &= m - 1) emit_tiles(__ffsll((long long)m) - 1, tid, PLAN_THREADS);
-  for (unsigned long long m = big1; m; m &= m - 1) emit_tiles(64 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
-  for (unsigned long long m = big2; m; m &= m - 1) emit_tiles(128 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
+  const unsigned long long skip0 = handed_over ? sm.vbig_ext[0] : 0, skip1 = handed_over ? sm.vbig_ext[1] : 0, skip2 = handed_over ? sm.vbig_ext[2] : 0;
+  for (unsigned long long m = big0 & ~skip0; m; m &= m - 1) emit_tiles(__ffsll((long long)m) - 1, tid, PLAN_THREADS);
+  for (unsigned long long m = big1 & ~skip1; m; m &= m - 1) emit_tiles(64 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
+  for (unsigned long long m = big2 & ~skip2; m; m &= m - 1) emit_tiles(128 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
   LB2_T(9);
 #ifdef LB2_PLAN_TIMING
   if (tid == 0 && f == 0) {
@@ -1766,6 +1797,23 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
 }
 
 #ifndef LB2_HOST_EMULATION  // (the CPU warp emulator under tests/emu compiles only the plan kernel)
+// ---------------------------------------------------------------- tiles of the very big extents
+// One CTA per recorded extent (grid-stride over the list), 256 threads striding over its tiles: the 54 000
+// descriptors of a 900 MB section are written by the whole GPU in a few microseconds.
+__global__ void __launch_bounds__(256) lb2_expand_kernel(const BigExt *big, uint32_t big_cap, const BatchCounters *ctr, Tile *tiles) {
+  if (ctr->overflow) return;
+  const uint32_t n = ctr->n_big < big_cap ? ctr->n_big : big_cap;
+  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+    const BigExt r = big[e];
+    const uint32_t cnt = (uint32_t)((r.dst + r.len - 1) / TILE_BYTES - r.dst / TILE_BYTES + 1);
+    Tile *out = tiles + r.tile_index;
+    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) out[k] = extent_tile(r.src, r.dst, r.len, r.file, k);
+  }
+}
+void launch_expand(const BigExt *big, uint32_t big_cap, const BatchCounters *ctr, Tile *tiles, int grid, cudaStream_t s) {
+  lb2_expand_kernel<<<grid, 256, 0, s>>>(big, big_cap, ctr, tiles);
+}
+
 // ---------------------------------------------------------------- output offsets
 // Exclusive scan of the 256-byte-rounded output sizes: where each stripped file starts in the
 // output arena.  One CTA; n_files is at most a few 10^5.
