@@ -52,7 +52,7 @@ TOTAL_FILES = 10000
 FILES_PER_GPU = 1250
 SEED = 0xB200
 SAMPLE_SPAN = 15 << 30        # host-side legs (e2e, tree, CPU baseline) work on the first <= 15 GiB of a shard
-LAUNCHES_PER_BATCH = 4        # plan, tile expansion of the very big extents, scan, compaction
+LAUNCHES_PER_BATCH = 3        # plan, scan (+ tile expansion of the very big extents), compaction
 
 
 def peaks():

@@ -43,7 +43,7 @@ struct Workspace {
   Tile *d_tiles = nullptr;
   BatchCounters *d_ctr = nullptr;
   UpRange *d_ranges = nullptr, *h_ranges = nullptr;  // host-buffer pipeline: input ranges to upload (pinned copy)
-  BigExt *d_big = nullptr;      // extents handed to lb2_expand_kernel
+  BigExt *d_big = nullptr;      // extents whose tiles the scan launch's extra CTAs write
   uint32_t cap_big = 0;
   uint32_t cap_ranges = 0;
   uint64_t *h_stage = nullptr;  // pinned: 2*(n+1) offsets/sizes up
@@ -254,17 +254,16 @@ static int enqueue_batch(lb2_ctx *ctx, Workspace &w, const uint8_t *d_in, const 
   pa.scratch = w.d_scratch; pa.out_size = w.d_out_size; pa.status = w.d_status;
   pa.tiles = w.d_tiles; pa.tile_cap = w.cap_tiles; pa.ctr = w.d_ctr;
   pa.up_ranges = export_ranges ? w.d_ranges : nullptr; pa.up_cap = export_ranges ? w.cap_ranges : 0;
-  if (w.cap_big < 4u * n + 1024u) {
+  if (w.cap_big < 8u * n + 4096u) {
     cudaFree(w.d_big);
     w.d_big = nullptr; w.cap_big = 0;
-    const uint32_t cap = 4u * std::max<uint32_t>(n, w.cap_files) + 1024u;
+    const uint32_t cap = 8u * std::max<uint32_t>(n, w.cap_files) + 4096u;
     CK(cudaMalloc(&w.d_big, (size_t)cap * sizeof(BigExt)));
     w.cap_big = cap;
   }
   pa.big = w.d_big; pa.big_cap = w.cap_big;
   launch_plan(pa, s);
-  launch_expand(w.d_big, w.cap_big, w.d_ctr, w.d_tiles, ctx->sm_count * 4, s);
-  launch_scan(w.d_out_size, w.d_out_off, n, compact ? out_cap : ~0ull, w.d_ctr, s);
+  launch_scan(w.d_out_size, w.d_out_off, n, compact ? out_cap : ~0ull, w.d_ctr, w.d_big, w.cap_big, w.d_tiles, ctx->sm_count * 2, s);
   CK(cudaEventRecord(w.ev[1], s));
   if (compact) {
     CompactArgs ca;

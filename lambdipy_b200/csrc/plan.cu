@@ -1748,17 +1748,31 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
   // whole grid (if its list is full the CTA writes them itself, as it does the other big ones)
   if (a.big && (sm.vbig_ext[0] | sm.vbig_ext[1] | sm.vbig_ext[2])) {
     if (tid == 0) {
-      const unsigned nvb = __popcll(sm.vbig_ext[0]) + __popcll(sm.vbig_ext[1]) + __popcll(sm.vbig_ext[2]);
-      const unsigned at0 = atomicAdd(&a.ctr->n_big, nvb);
-      if (at0 + nvb <= a.big_cap) {
+      // one record per <= BIG_PART_TILES tiles, so that a 900 MB section becomes 27 work items for the grid
+      unsigned nrec = 0;
+      for (int w = 0; w < 3; w++)
+        for (unsigned long long m = sm.vbig_ext[w]; m; m &= m - 1) {
+          const int e = 64 * w + __ffsll((long long)m) - 1;
+          const uint64_t d = sm.u.x.dst[e], l = sm.u.x.len[e];
+          const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - d / TILE_BYTES + 1);
+          nrec += (cnt + BIG_PART_TILES - 1) / BIG_PART_TILES;
+        }
+      const unsigned at0 = atomicAdd(&a.ctr->n_big, nrec);
+      if (at0 + nrec <= a.big_cap) {
         unsigned at = at0;
         for (int w = 0; w < 3; w++)
           for (unsigned long long m = sm.vbig_ext[w]; m; m &= m - 1) {
             const int e = 64 * w + __ffsll((long long)m) - 1;
-            BigExt r;
-            r.src = sm.u.x.src[e]; r.dst = sm.u.x.dst[e]; r.len = sm.u.x.len[e];
-            r.tile_index = tile_base + sm.u.x.tiles[e]; r.file = f; r.pad = 0;
-            a.big[at++] = r;
+            const uint64_t sr = sm.u.x.src[e], d = sm.u.x.dst[e], l = sm.u.x.len[e], t0 = d / TILE_BYTES;
+            const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - t0 + 1);
+            for (uint32_t k0 = 0; k0 < cnt; k0 += BIG_PART_TILES) {
+              const uint32_t k1 = k0 + BIG_PART_TILES < cnt ? k0 + BIG_PART_TILES : cnt;
+              const uint64_t b0 = k0 ? (t0 + k0) * TILE_BYTES : d, b1 = k1 < cnt ? (t0 + k1) * TILE_BYTES : d + l;
+              BigExt r;
+              r.src = sr ? sr + (b0 - d) : 0; r.dst = b0; r.len = b1 - b0;
+              r.tile_index = tile_base + sm.u.x.tiles[e] + k0; r.file = f; r.pad = 0;
+              a.big[at++] = r;
+            }
           }
         sm.vbig_taken = 1;
       }
@@ -1797,28 +1811,26 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
 }
 
 #ifndef LB2_HOST_EMULATION  // (the CPU warp emulator under tests/emu compiles only the plan kernel)
-// ---------------------------------------------------------------- tiles of the very big extents
-// One CTA per recorded extent (grid-stride over the list), 256 threads striding over its tiles: the 54 000
-// descriptors of a 900 MB section are written by the whole GPU in a few microseconds.
-__global__ void __launch_bounds__(256) lb2_expand_kernel(const BigExt *big, uint32_t big_cap, const BatchCounters *ctr, Tile *tiles) {
-  if (ctr->overflow) return;
-  const uint32_t n = ctr->n_big < big_cap ? ctr->n_big : big_cap;
-  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
-    const BigExt r = big[e];
-    const uint32_t cnt = (uint32_t)((r.dst + r.len - 1) / TILE_BYTES - r.dst / TILE_BYTES + 1);
-    Tile *out = tiles + r.tile_index;
-    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) out[k] = extent_tile(r.src, r.dst, r.len, r.file, k);
-  }
-}
-void launch_expand(const BigExt *big, uint32_t big_cap, const BatchCounters *ctr, Tile *tiles, int grid, cudaStream_t s) {
-  lb2_expand_kernel<<<grid, 256, 0, s>>>(big, big_cap, ctr, tiles);
-}
-
 // ---------------------------------------------------------------- output offsets
-// Exclusive scan of the 256-byte-rounded output sizes: where each stripped file starts in the
-// output arena.  One CTA; n_files is at most a few 10^5.
+// Block 0: exclusive scan of the 256-byte-rounded output sizes -- where each stripped file starts in the output
+// arena (one CTA; n_files is at most a few 10^5).
+// Blocks 1..: the tiles of the very big extents the plan kernel only recorded (PlanArgs::big), one record of at most
+// BIG_PART_TILES tiles per CTA-iteration: the 54 000 descriptors of a 900 MB section are written by the whole GPU
+// while block 0 scans -- same launch, so small batches pay nothing for it.
 __global__ void __launch_bounds__(1024) lb2_scan_kernel(const uint64_t *out_size, uint64_t *out_off, uint32_t n,
-                                                         uint64_t out_cap, BatchCounters *ctr) {
+                                                         uint64_t out_cap, BatchCounters *ctr, const BigExt *big, uint32_t big_cap,
+                                                         Tile *tiles) {
+  if (blockIdx.x > 0) {
+    if (!big || ctr->overflow) return;
+    const uint32_t nb = ctr->n_big < big_cap ? ctr->n_big : big_cap;
+    for (uint32_t e = blockIdx.x - 1; e < nb; e += gridDim.x - 1) {
+      const BigExt r = big[e];
+      const uint32_t cnt = (uint32_t)((r.dst + r.len - 1) / TILE_BYTES - r.dst / TILE_BYTES + 1);
+      Tile *out = tiles + r.tile_index;
+      for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) out[k] = extent_tile(r.src, r.dst, r.len, r.file, k);
+    }
+    return;
+  }
   __shared__ uint64_t warp_excl[32];
   __shared__ uint64_t carry, block_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1856,8 +1868,9 @@ void launch_plan(const PlanArgs &a, cudaStream_t s) {
   if (!a.n_files) return;
   lb2_plan_kernel<<<a.n_files, PLAN_THREADS, 0, s>>>(a);  // one CTA per file, one launch for every file
 }
-void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, cudaStream_t s) {
-  lb2_scan_kernel<<<1, 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr);
+void launch_scan(const uint64_t *out_size, uint64_t *out_off, uint32_t n, uint64_t out_cap, BatchCounters *ctr, const BigExt *big,
+                 uint32_t big_cap, Tile *tiles, int expand_ctas, cudaStream_t s) {
+  lb2_scan_kernel<<<1 + (big ? expand_ctas : 0), 1024, 0, s>>>(out_size, out_off, n, out_cap, ctr, big, big_cap, tiles);
 }
 
 #endif  // LB2_HOST_EMULATION

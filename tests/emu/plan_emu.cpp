@@ -108,12 +108,12 @@ extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8
   PlanArgs a;
   a.in = arena; a.in_off = &in_off; a.in_size = &in_size; a.n_files = 1; a.flags = flags;
   a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr; a.up_ranges = nullptr; a.up_cap = 0;
-  std::vector<BigExt> big(64);
+  std::vector<BigExt> big(256);
   a.big = big.data(); a.big_cap = (uint32_t)big.size();
   run_block(a);
   int rc = status;
   if (status == ST_OK && !ctr.overflow) {
-    // what lb2_expand_kernel does on the device: the tiles of the extents the planner only recorded
+    // what the extra CTAs of the scan launch do on the device: the tiles of the extents the planner only recorded
     for (uint32_t e = 0; e < ctr.n_big && e < a.big_cap; e++) {
       const BigExt &r = big[e];
       const uint32_t cnt = (uint32_t)((r.dst + r.len - 1) / TILE_BYTES - r.dst / TILE_BYTES + 1);
