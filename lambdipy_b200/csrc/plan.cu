@@ -456,7 +456,9 @@ __device__ void group_fix_nested_classes(PlanSmem &sm, const uint8_t *nbuf, int 
   const DNote *__restrict__ notes = sm.u.n.notes;
   uint16_t *__restrict__ perm = sm.u.n.perm;
   uint16_t *__restrict__ tmp = sm.u.n.tmp;
-  for (int rep = t; rep < n; rep += NT) {
+  // each replay is a private sequential loop: threads of one warp that run different replays are serialised by the
+  // hardware, so neighbouring representatives (the first notes of a section, typically) go to different warps
+  for (int rep = (NT == 32) ? t : ((t & 31) * (NT / 32) + (t >> 5)); rep < n; rep += NT) {
     if (notes[rep].cls != rep || !notes[rep].pad) continue;
     // the attribute's stretch of perm[]
     int p0 = 0;
