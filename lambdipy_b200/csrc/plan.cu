@@ -984,6 +984,23 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
               }
             }
           }
+          // gate: a TLS NOBITS section (.tbss) must sit where the linker puts it -- at the aligned end of the TLS section
+          // before it, or at the start of PT_TLS.  BFD derives the file offset it writes for .tbss from that address;
+          // only the natural placement is reproduced (found by header fuzzing: sh_addr moved by 4 bytes -> other sh_offset)
+          if (alloc && (h.sh_flags & SHF_TLS) && h.sh_type == SHT_NOBITS) {
+            const uint64_t al = h.sh_addralign ? h.sh_addralign : 1;
+            if (al & (al - 1)) err_uns = 1;
+            int pj = -1;
+            for (int j = i - 1; j >= 1; j--)
+              if ((sm.sh[j].sh_flags & SHF_TLS) && (sm.sh[j].sh_flags & SHF_ALLOC)) { pj = j; break; }
+            if (pj >= 0) {
+              const uint64_t pe = sm.sh[pj].sh_addr + sm.sh[pj].sh_size;
+              if (h.sh_addr < pe || h.sh_addr - pe >= al || (h.sh_addr & (al - 1))) err_uns = 1;
+            } else {
+              for (int j = 0; j < phnum; j++)
+                if (sm.ph[j].p_type == PT_TLS && h.sh_addr != sm.ph[j].p_vaddr) err_uns = 1;
+            }
+          }
           is_keep = drop ? 0 : 1;
           is_alloc = alloc;
           is_nobits = h.sh_type == SHT_NOBITS;

@@ -554,6 +554,24 @@ int lbo_strip(const uint8_t *in, uint64_t n, uint8_t **out_p, uint64_t *out_n, u
           break;
       }
     }
+    /* gate: a TLS NOBITS section (.tbss) must sit where the linker puts it -- at the aligned end of the TLS section
+     * before it (or at the start of PT_TLS).  BFD derives the file offset it writes for .tbss from that address
+     * (probe: .tbss sh_addr moved by 4 / 16 / 256 bytes -> sh_offset 0x2dc8 / 0x2dd0 / 0x2f90 instead of 0x2db4);
+     * only the natural placement is reproduced. */
+    if ((h->sh_flags & SHF_TLS) && (h->sh_flags & SHF_ALLOC) && h->sh_type == SHT_NOBITS) {
+      uint64_t al = h->sh_addralign ? h->sh_addralign : 1;
+      if (al & (al - 1)) UNSUP();
+      int64_t pj = -1;
+      for (int64_t j = (int64_t)i - 1; j >= 1; j--)
+        if ((S[j].h.sh_flags & SHF_TLS) && (S[j].h.sh_flags & SHF_ALLOC)) { pj = j; break; }
+      if (pj >= 0) {
+        uint64_t pe = S[pj].h.sh_addr + S[pj].h.sh_size;
+        if (h->sh_addr < pe || h->sh_addr - pe >= al || (h->sh_addr & (al - 1))) UNSUP();
+      } else {
+        for (uint64_t j = 0; j < phnum; j++)
+          if (P[j].p_type == PT_TLS && h->sh_addr != P[j].p_vaddr) UNSUP();
+      }
+    }
     S[i].keep = !drop;
     /* BFD keeps alignment as a power of two that the section address honours
      * (probe: doctored sh_addralign 0/3/24/4096 -> min(lowbit(align), lowbit(addr)), 0 -> 1). */

@@ -123,3 +123,28 @@ def test_corrupt_note_sections(emu, oracle, variants, fixture_dir):
         st, out = emu.strip(_read(p))
         rc, _ = oracle.strip(_read(p))
         assert st == 7 and rc == 7, (sz, st, rc)
+
+
+def test_misplaced_tbss_is_declined_by_planner_and_oracle(emu, oracle, tmp_path):
+    """BFD derives the sh_offset it writes for .tbss from the section's address; only the linker's placement (aligned
+    end of .tdata) is reproduced, anything else goes to the host strip (gate found by header fuzzing)."""
+    import struct
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text("__thread int a = 5; __thread int b; __thread char big[100];\nint f(void){ return a + b + big[3]; }\n")
+    so = tmp_path / "t.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-g", "-o", str(so), str(src)], check=True)
+    data = bytearray(so.read_bytes())
+    shoff, = struct.unpack_from("<Q", data, 0x28)
+    shnum, shstr = struct.unpack_from("<HH", data, 0x3c)
+    so_, ss_ = struct.unpack_from("<QQ", data, shoff + shstr * 64 + 24)
+    names = bytes(data[so_:so_ + ss_])
+    tb = [i for i in range(shnum) if names[struct.unpack_from("<I", data, shoff + i * 64)[0]:].split(b"\0")[0] == b".tbss"][0]
+    addr, = struct.unpack_from("<Q", data, shoff + tb * 64 + 16)
+    assert _agree(emu, oracle, bytes(data)) == 0                      # the natural file takes the device path
+    gnu, _ = F.gnu_strip_bytes(str(so), str(tmp_path))
+    assert emu.strip(bytes(data))[1] == gnu
+    for delta in (4, 16, -4, 256):
+        d = bytearray(data)
+        struct.pack_into("<Q", d, shoff + tb * 64 + 16, addr + delta)
+        assert oracle.strip(bytes(d))[0] == 6 and emu.strip(bytes(d))[0] == 6, delta
