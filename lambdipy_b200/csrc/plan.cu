@@ -80,6 +80,9 @@ struct PlanSmem {
   uint8_t order[MAX_SH + 1];
   uint8_t pkeep[MAX_PH];
   uint8_t piece[MAX_SH + 1];
+  uint32_t ord_hash[MAX_SH + 1]; // name hash / length per OUTPUT position: the name searches below read them in a row
+  uint16_t ord_len[MAX_SH + 1];
+  uint64_t pos_off[MAX_SH + 1];  // new offset of the content section at each output position, ~0 for the others (phase L)
   uint16_t name_len[MAX_SH];     // strlen of each section's name
   uint32_t name_hash[MAX_SH];    // FNV-1a of each section's name: cheap inequality test
   char names[MAX_STR + 48];      // + ".shstrtab" literal + slack for the 24-byte name loads
@@ -1042,6 +1045,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       const int k = __popcll(keepmask & ((1ull << tid) - 1));
       sm.new_index[tid] = (uint8_t)k;
       sm.order[k] = (uint8_t)tid;
+      sm.ord_hash[k] = sm.name_hash[tid]; sm.ord_len[k] = sm.name_len[tid];
     }
     if (tid == 0) sm.nk = __popcll(keepmask);
   } else if (tid == 0) {
@@ -1059,7 +1063,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       sm.order[nk++] = (uint8_t)i;
       emitted |= 1ull << i;
     }
-    for (int k = 0; k < nk; k++) sm.new_index[sm.order[k]] = (uint8_t)k;
+    for (int k = 0; k < nk; k++) {
+      sm.new_index[sm.order[k]] = (uint8_t)k;
+      sm.ord_hash[k] = sm.name_hash[sm.order[k]]; sm.ord_len[k] = sm.name_len[sm.order[k]];
+    }
     sm.nk = nk;
   }
   // ---- F1. which kept sections each program header carries: one header per warp-iteration, two ballots
@@ -1320,9 +1327,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       int first = k;
       const uint32_t hh = sm.name_hash[i];
       if (sm.name_len[i] == 9 && d_streq(nm, sm.names + strsz)) first = 0;  // a kept section that is itself called .shstrtab
-      else for (int q = 1; q < k; q++) {
-        const int oi = sm.order[q];
-        if (sm.name_hash[oi] == hh && sm.name_len[oi] == sm.name_len[i] && d_streq(nm, sm.names + sm.sh[oi].sh_name)) { first = q; break; }
+      else {
+        const uint16_t ll = sm.name_len[i];
+        for (int q = 1; q < k; q++)
+          if (sm.ord_hash[q] == hh && sm.ord_len[q] == ll && d_streq(nm, sm.names + sm.sh[sm.order[q]].sh_name)) { first = q; break; }
       }
       sm.piece[k] = (uint8_t)first;  // order position of the first section with this name
     }
@@ -1557,10 +1565,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
           auto find_name = [&](const char *want) {
             int wl;
             const uint32_t wh = d_hash(want, &wl);
-            for (int q = 1; q < nk; q++) {
-              const int oi = sm.order[q];
-              if (sm.name_hash[oi] == wh && sm.name_len[oi] == wl && d_streq(sm.names + sm.sh[oi].sh_name, want)) return q;
-            }
+            for (int q = 1; q < nk; q++)
+              if (sm.ord_hash[q] == wh && sm.ord_len[q] == wl && d_streq(sm.names + sm.sh[sm.order[q]].sh_name, want)) return q;
             return -1;
           };
           if (d_streq(t, ".plt")) {
@@ -1585,6 +1591,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       }
     }
     *reinterpret_cast<Shdr *>(scr + SCR_SHDR + (uint32_t)k * 64) = h;
+    // for phase L: where this position's contents go, if it has any
+    sm.pos_off[k] = (k >= 1 && k < nk && h.sh_type != SHT_NOBITS && h.sh_size != 0) ? h.sh_offset : ~0ull;
   }
   if (tid >= 96 && tid - 96 < phnum && sm.pkeep[tid - 96]) {   // warp 3: the surviving program headers, compacted
     const int j = tid - 96;
@@ -1608,17 +1616,17 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
   //         copied from the scratch slot, or zero-filled (BFD leaves gaps as file holes).
   // pieces = [headers] + content sections sorted by new offset + [.shstrtab] + [section table].  Rank sort,
   // one kept section per thread (the keys are distinct unless sections overlap, which the gap check rejects).
+  __syncthreads();   // pos_off[] of phase K
   {
     bool content = false;
     int i = 0;
-    if (tid >= 1 && tid < nk) { i = sm.order[tid]; content = sm.sh[i].sh_type != SHT_NOBITS && sm.new_size[i] != 0; }
+    if (tid >= 1 && tid < nk) { i = sm.order[tid]; content = sm.pos_off[tid] != ~0ull; }
     if (content) {
-      const uint64_t mine = sm.new_off[i];
+      const uint64_t mine = sm.pos_off[tid];
       int r = 0;
+#pragma unroll 4
       for (int q = 1; q < nk; q++) {
-        const int oi = sm.order[q];
-        if (q == tid || sm.sh[oi].sh_type == SHT_NOBITS || sm.new_size[oi] == 0) continue;
-        const uint64_t o = sm.new_off[oi];
+        const uint64_t o = sm.pos_off[q];   // ~0 for positions without contents: never "before"
         r += (o < mine) || (o == mine && q < tid);
       }
       sm.piece[1 + r] = (uint8_t)i;
