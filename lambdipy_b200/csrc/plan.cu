@@ -103,6 +103,7 @@ struct PlanSmem {
   unsigned long long tile_base;
   unsigned long long big_ext[3];  // bit e: extent e has more than 64 tiles (MAX_EXT = 140 extents)
   unsigned long long vbig_ext[3]; // ... more than BIG_EXT_TILES tiles
+  unsigned long long mid_ext[3];  // bit e: extent e has 5..64 tiles
   int vbig_taken;                 // the expand kernel's list had room: the CTA does not write those tiles itself
   uint32_t n_tiles;
 #ifdef LB2_PLAN_TIMING
@@ -1650,10 +1651,12 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     int ne = 0, bad = 0;
     unsigned long long big0 = 0, big1 = 0, big2 = 0;   // extents with > 64 tiles (bit = extent index, MAX_EXT = 140)
     unsigned long long vb0 = 0, vb1 = 0, vb2 = 0;      // ... of which more than BIG_EXT_TILES: candidates for the expand kernel
+    unsigned long long md0 = 0, md1 = 0, md2 = 0;      // extents with 5..64 tiles: one warp each (<= 4 tiles: one thread each)
     auto mark_big = [&](int at, uint32_t c) {
       if (at < 64) big0 |= 1ull << at; else if (at < 128) big1 |= 1ull << (at - 64); else big2 |= 1ull << (at - 128);
       if (c > BIG_EXT_TILES) { if (at < 64) vb0 |= 1ull << at; else if (at < 128) vb1 |= 1ull << (at - 64); else vb2 |= 1ull << (at - 128); }
     };
+    auto mark_mid = [&](int at) { if (at < 64) md0 |= 1ull << at; else if (at < 128) md1 |= 1ull << (at - 64); else md2 |= 1ull << (at - 128); };
     unsigned long long copy_bytes = 0;
     uint32_t running = 0;
     for (int q0 = 0; q0 < total_pieces; q0 += 32) {
@@ -1680,11 +1683,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
         uint32_t t0 = running + inc - (cnt_gap + cnt);
         if (gap) {  // file hole
           x.src[at] = 0; x.dst[at] = prev_end; x.len[at] = dst - prev_end; x.tiles[at] = t0; t0 += cnt_gap;
-          if (cnt_gap > 64) mark_big(at, cnt_gap);
+          if (cnt_gap > 64) mark_big(at, cnt_gap); else if (cnt_gap > 4) mark_mid(at);
           at++;
         }
         x.src[at] = src; x.dst[at] = dst; x.len[at] = len; x.tiles[at] = t0;
-        if (cnt > 64) mark_big(at, cnt);
+        if (cnt > 64) mark_big(at, cnt); else if (cnt > 4) mark_mid(at);
         copy_bytes += len;
       }
       running += __shfl_sync(0xffffffffu, inc, 31);
@@ -1700,11 +1703,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
       vb0 |= __shfl_xor_sync(0xffffffffu, vb0, o);
       vb1 |= __shfl_xor_sync(0xffffffffu, vb1, o);
       vb2 |= __shfl_xor_sync(0xffffffffu, vb2, o);
+      md0 |= __shfl_xor_sync(0xffffffffu, md0, o);
+      md1 |= __shfl_xor_sync(0xffffffffu, md1, o);
+      md2 |= __shfl_xor_sync(0xffffffffu, md2, o);
     }
     const bool any_bad = __ballot_sync(0xffffffffu, bad) != 0;
     if (lane == 0) {
       sm.n_ext = ne; sm.copy_bytes = copy_bytes; sm.n_tiles = running; sm.big_ext[0] = big0; sm.big_ext[1] = big1; sm.big_ext[2] = big2;
       sm.vbig_ext[0] = vb0; sm.vbig_ext[1] = vb1; sm.vbig_ext[2] = vb2; sm.vbig_taken = 0;
+      sm.mid_ext[0] = md0; sm.mid_ext[1] = md1; sm.mid_ext[2] = md2;
       if (any_bad) sm.fail = ST_UNSUPPORTED_LAYOUT;
       else sm.tile_base = atomicAdd(&a.ctr->n_tiles, (unsigned long long)running);   // one atomicAdd per file reserves the range
     }
@@ -1807,13 +1814,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) lb2_plan_kernel(PlanArgs a) {
     __syncthreads();
   }
   const bool handed_over = sm.vbig_taken != 0;
-  // small extents: one per warp (a thread only looks at its warp's share of the list); the few extents
-  // with hundreds of tiles were set aside by phase L and are written by the whole CTA
+  // extents of up to 4 tiles (most of them: headers, tables, small sections, gaps): one THREAD each; 5..64 tiles: one
+  // warp each; the few with hundreds of tiles were set aside by phase L and are written by the whole CTA
   const unsigned long long big0 = sm.big_ext[0], big1 = sm.big_ext[1], big2 = sm.big_ext[2];
-  for (int e = warp; e < n_ext; e += PLAN_THREADS / 32) {
-    const bool big = ((e < 64 ? big0 >> e : (e < 128 ? big1 >> (e - 64) : big2 >> (e - 128))) & 1) != 0;
-    if (!big) emit_tiles(e, lane, 32);
+  for (int e = tid; e < n_ext; e += PLAN_THREADS) {
+    const uint64_t d = sm.u.x.dst[e], l = sm.u.x.len[e], s = sm.u.x.src[e];
+    if (l == 0) continue;
+    const uint32_t cnt = (uint32_t)((d + l - 1) / TILE_BYTES - d / TILE_BYTES + 1);
+    if (cnt > 4) continue;
+    Tile *out = a.tiles + tile_base + sm.u.x.tiles[e];
+    for (uint32_t k = 0; k < cnt; k++) out[k] = extent_tile(s, d, l, f, k);
   }
+  for (int w = 0; w < 3; w++)
+    for (unsigned long long m = sm.mid_ext[w]; m; m &= m - 1) {
+      const int e = 64 * w + __ffsll((long long)m) - 1;
+      if ((e & (PLAN_THREADS / 32 - 1)) == warp) emit_tiles(e, lane, 32);
+    }
   const unsigned long long skip0 = handed_over ? sm.vbig_ext[0] : 0, skip1 = handed_over ? sm.vbig_ext[1] : 0, skip2 = handed_over ? sm.vbig_ext[2] : 0;
   for (unsigned long long m = big0 & ~skip0; m; m &= m - 1) emit_tiles(__ffsll((long long)m) - 1, tid, PLAN_THREADS);
   for (unsigned long long m = big1 & ~skip1; m; m &= m - 1) emit_tiles(64 + __ffsll((long long)m) - 1, tid, PLAN_THREADS);
