@@ -108,8 +108,11 @@ extern "C" int lb2emu_strip(const uint8_t *in, uint64_t n, uint32_t flags, uint8
   PlanArgs a;
   a.in = arena; a.in_off = &in_off; a.in_size = &in_size; a.n_files = 1; a.flags = flags;
   a.scratch = scratch; a.out_size = &out_size; a.status = &status; a.tiles = tiles.data(); a.tile_cap = tile_cap; a.ctr = &ctr; a.up_ranges = nullptr; a.up_cap = 0;
+  // (LB2EMU_BIG_CAP=0 leaves no room in the list: the planning CTA then writes the tiles of huge extents itself)
+  const char *cap_env = getenv("LB2EMU_BIG_CAP");
   std::vector<BigExt> big(256);
-  a.big = big.data(); a.big_cap = (uint32_t)big.size();
+  const uint32_t big_cap_used = cap_env ? (uint32_t)atoi(cap_env) : (uint32_t)big.size();
+  a.big = big.data(); a.big_cap = big_cap_used < big.size() ? big_cap_used : (uint32_t)big.size();
   run_block(a);
   int rc = status;
   if (status == ST_OK && !ctr.overflow) {

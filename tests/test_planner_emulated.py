@@ -148,3 +148,23 @@ def test_misplaced_tbss_is_declined_by_planner_and_oracle(emu, oracle, tmp_path)
         d = bytearray(data)
         struct.pack_into("<Q", d, shoff + tb * 64 + 16, addr + delta)
         assert oracle.strip(bytes(d))[0] == 6 and emu.strip(bytes(d))[0] == 6, delta
+
+
+def test_huge_extents_with_and_without_room_in_the_expand_list(emu, oracle, monkeypatch):
+    """Extents of more than 512 tiles are normally only recorded (the scan launch's extra CTAs write their tiles, in
+    parts of 2048); when the list is full the planning CTA writes them itself.  Both routes must tile the output exactly."""
+    from lambdipy_b200.corpus import Corpus
+    c = Corpus(2, seed=31, min_size=40 << 20, max_size=48 << 20)      # .text / .debug_info extents of 8+ MB
+    for i in range(len(c)):
+        data = c.materialize(i)
+        rc, want = oracle.strip(data)
+        assert rc == 0
+        st, got = emu.strip(data)
+        assert st == 0 and got == want
+        monkeypatch.setenv("LB2EMU_BIG_CAP", "0")
+        st, got = emu.strip(data)
+        assert st == 0 and got == want
+        monkeypatch.setenv("LB2EMU_BIG_CAP", "3")                      # room for some files' records only
+        st, got = emu.strip(data)
+        assert st == 0 and got == want
+        monkeypatch.delenv("LB2EMU_BIG_CAP")
